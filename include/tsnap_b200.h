@@ -1,0 +1,214 @@
+/*
+ * tsnap_b200 — C ABI of the B200-native checkpoint data plane.
+ *
+ * This is the drop-in boundary for ONE path of pytorch/torchsnapshot: the device->host drain and
+ * serialization of tensor state on save, and its mirror on restore.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree, "T:" = torchsnapshot/).
+ * The reference is 100% Python, so a maintainer binds these with ctypes; the
+ * signatures use only plain pointers, sizes and integer handles — no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative TSNAP_E* code on failure;
+ *     tsnap_last_error() returns a thread-local, human-readable message for the last failure.
+ *   - all functions are callable from any thread and never take the Python GIL.
+ *   - "wire buffer" = the byte image the reference would have produced for one storage object
+ *     (one WriteReq / one file): raw C-contiguous native-endian element bytes of each member, back to
+ *     back at their byte_range, no header, no padding (T:serialization.py:177-204, T:batcher.py:307).
+ */
+#ifndef TSNAP_B200_H_
+#define TSNAP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSNAP_ABI_VERSION 1
+#define TSNAP_MAX_DIMS 8
+
+/* error codes */
+#define TSNAP_OK 0
+#define TSNAP_EINVAL (-1)   /* bad argument / malformed descriptor          */
+#define TSNAP_ECUDA (-2)    /* a CUDA runtime call failed (no GPU, OOM, ..)   */
+#define TSNAP_EIO (-3)      /* open/pwrite/pread failed                      */
+#define TSNAP_ENOMEM (-4)   /* host allocation failed                        */
+#define TSNAP_ESTATE (-5)   /* call made in the wrong job state              */
+#define TSNAP_EUNSUP (-6)   /* dtype pair / layout not supported             */
+
+/* element types: the ten buffer-protocol dtypes of T:serialization.py:162-173 (raw path).  The
+ * enum value only selects element size and, when src_dtype != dst_dtype, the conversion. */
+enum tsnap_dtype {
+    TSNAP_U8 = 0,   /* torch.uint8 / torch.bool (1-byte payload, copied verbatim) */
+    TSNAP_I8 = 1,
+    TSNAP_I16 = 2,
+    TSNAP_I32 = 3,
+    TSNAP_I64 = 4,
+    TSNAP_F16 = 5,
+    TSNAP_BF16 = 6,
+    TSNAP_F32 = 7,
+    TSNAP_F64 = 8,
+    TSNAP_BOOL = 9,
+    TSNAP_DTYPE_COUNT = 10
+};
+
+/* where a side of a copy lives */
+enum tsnap_space {
+    TSNAP_SPACE_DEVICE = 0, /* addr is a device pointer on the engine's GPU                 */
+    TSNAP_SPACE_HOST = 1,   /* addr is a host pointer (CPU tensor)                          */
+    TSNAP_SPACE_WIRE = 2    /* addr is a byte offset inside the wire buffer of the file    */
+};
+
+/*
+ * One strided view <-> strided view copy of identical logical shape.  It is the common currency
+ * of both directions:
+ *   save    : src = live tensor view (DEVICE or HOST), dst = WIRE, dst_strides ignored (the wire
+ *             image is the C-contiguous layout of `sizes` starting at dst_addr).
+ *             Replaces the body of TensorBufferStager.stage_buffer (T:io_preparers/tensor.py:240-271)
+ *             and the per-member .contiguous()+copy_ of GPUBatchedBufferStager.stage_buffer
+ *             (T:batcher.py:144-159) / BatchedBufferStager.stage_buffer (T:batcher.py:66-93).
+ *   restore : src = WIRE with src_strides describing the saved piece's C-contiguous layout
+ *             (possibly a sub-box of it: reshard-on-load), dst = live tensor view.
+ *             Replaces TensorBufferConsumer.consume_buffer (T:io_preparers/tensor.py:331-340) and
+ *             the narrow()+tensor_copy loop of ShardedTensorBufferConsumer.consume_buffer
+ *             (T:io_preparers/sharded_tensor.py:310-323, get_views :285-298).
+ * Strides are in ELEMENTS of the respective dtype, as torch reports them; may be 0 or negative is
+ * NOT supported (torch never produces negative strides).
+ */
+typedef struct tsnap_copy_desc {
+    uint64_t src_addr;
+    uint64_t dst_addr;
+    int64_t sizes[TSNAP_MAX_DIMS];
+    int64_t src_strides[TSNAP_MAX_DIMS];
+    int64_t dst_strides[TSNAP_MAX_DIMS];
+    int32_t ndim;
+    int32_t src_dtype;  /* enum tsnap_dtype */
+    int32_t dst_dtype;  /* enum tsnap_dtype; != src_dtype fuses a cast (north star "cast in the pack kernel") */
+    int32_t src_space;  /* enum tsnap_space */
+    int32_t dst_space;  /* enum tsnap_space */
+    int32_t reserved;
+} tsnap_copy_desc;
+
+typedef struct tsnap_engine tsnap_engine;
+typedef struct tsnap_job tsnap_job;
+
+typedef struct tsnap_engine_config {
+    int32_t device;            /* CUDA device ordinal; -1 = host-only engine (CPU tensors only)     */
+    int32_t io_threads;        /* native pwrite/pread workers (reference: <=16 concurrent I/Os,
+                                  T:knobs.py:38); 0 = default 16                                     */
+    uint64_t pinned_slot_bytes; /* size of one pinned ring slot; 0 = default 32 MiB                  */
+    int32_t pinned_slots;      /* ring depth; 0 = default 32 (=> 1 GiB pinned, allocated once)       */
+    int32_t flags;             /* TSNAP_ENGINE_* */
+    uint64_t hbm_staging_bytes; /* cap of the HBM staging arena; 0 = default (grow to payload, keep
+                                  >= 1/8 of HBM free)                                                */
+} tsnap_engine_config;
+
+#define TSNAP_ENGINE_NO_BULK 1u   /* force the LSU kernel for every tile (A/B for the ncu captures) */
+#define TSNAP_ENGINE_FSYNC 2u     /* fsync each file before the job reports completion ("durable") */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int tsnap_abi_version(void);
+const char* tsnap_last_error(void);
+size_t tsnap_dtype_size(int dtype);
+
+/* ---- engine: owns streams, the pinned ring, the HBM staging arena and the I/O workers.
+ * Replaces the per-call ThreadPoolExecutor(4) + asyncio state machine of execute_write_reqs /
+ * execute_read_reqs (T:scheduler.py:222-339, 386-446) for the requests it is given. */
+int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out);
+int tsnap_engine_destroy(tsnap_engine* eng);
+/* release cached pinned/HBM memory kept between jobs */
+int tsnap_engine_trim(tsnap_engine* eng);
+
+typedef struct tsnap_engine_stats {
+    uint64_t pinned_bytes;       /* pinned host bytes currently owned                 */
+    uint64_t hbm_arena_bytes;    /* HBM staging arena bytes currently owned           */
+    uint64_t kernels_launched;   /* cumulative count of tsnap kernel launches         */
+    uint64_t bytes_d2h;          /* cumulative                                        */
+    uint64_t bytes_h2d;          /* cumulative                                        */
+    uint64_t bytes_written;      /* cumulative bytes handed to pwrite                 */
+    uint64_t bytes_read;         /* cumulative bytes obtained from pread              */
+    int32_t sm_count;
+    int32_t device;
+} tsnap_engine_stats;
+int tsnap_engine_get_stats(tsnap_engine* eng, tsnap_engine_stats* out);
+
+/* ---- save job: {files, members} -> pack kernel -> pinned ring -> pwrite ------------------------
+ * One job == the WriteReqs of one Snapshot.take / async_take on this rank that carry raw tensor
+ * bytes (buffer_protocol serializer).  add_file == one WriteReq.path (T:io_types.py:34-37);
+ * add_member == one (byte_range, TensorBufferStager) pair of a slab (T:batcher.py:190-202) or the
+ * single member of an un-batched tensor/chunk/shard piece.                                        */
+int tsnap_save_job_create(tsnap_engine* eng, tsnap_job** out);
+/* path: absolute file path (parent directories are created).  nbytes: exact size of the wire image. */
+int tsnap_save_job_add_file(tsnap_job* job, const char* path, uint64_t nbytes, int32_t* file_index);
+/* desc->dst_space must be TSNAP_SPACE_WIRE; desc->dst_addr = byte offset of the member in the file. */
+int tsnap_save_job_add_member(tsnap_job* job, int32_t file_index, const tsnap_copy_desc* desc);
+/* Plans, launches the pack kernels on the engine's pack stream (ordered after everything already
+ * enqueued on `producer_stream`, a cudaStream_t passed as void*; NULL = legacy default stream) and
+ * starts the drain.  Returns immediately. */
+int tsnap_save_job_submit(tsnap_job* job, void* producer_stream);
+/* Blocks until every read of the source tensors has completed — the async_take return gate
+ * (T:snapshot.py:230-317 returns when all write requests are staged, T:scheduler.py:299). */
+int tsnap_job_wait_device(tsnap_job* job);
+/* Blocks until every file of the job is written (PendingIOWork.complete, T:scheduler.py:196-216). */
+int tsnap_job_wait(tsnap_job* job);
+/* 1 when finished (successfully or not), 0 otherwise */
+int tsnap_job_done(tsnap_job* job);
+int tsnap_job_destroy(tsnap_job* job);
+
+typedef struct tsnap_job_stats {
+    uint64_t payload_bytes;     /* sum of wire bytes of all files                          */
+    uint64_t n_files, n_members, n_tiles_bulk, n_tiles_lsu;
+    uint64_t n_kernel_launches;
+    double plan_ms;             /* host time spent normalising descriptors + building tables */
+    double kernel_ms;           /* CUDA-event time of the pack/unpack kernels (sum)          */
+    double kernel_bulk_ms, kernel_lsu_ms;
+    double device_done_ms;      /* submit -> all device reads complete (blocking window)     */
+    double total_ms;            /* submit -> job complete                                    */
+    uint64_t table_h2d_bytes;   /* descriptor/tile tables copied host->device                */
+} tsnap_job_stats;
+int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
+
+/* ---- load job: pread -> pinned ring -> H2D -> unpack/scatter kernel ---------------------------
+ * add_file == one (batched) ReadReq: path + byte range (T:io_types.py:52-56, merged per file like
+ * batch_read_requests T:batcher.py:387-478); add_member == one destination region, with
+ * desc->src_space == TSNAP_SPACE_WIRE and desc->src_addr relative to `offset`.                  */
+int tsnap_load_job_create(tsnap_engine* eng, tsnap_job** out);
+int tsnap_load_job_add_file(tsnap_job* job, const char* path, uint64_t offset, uint64_t nbytes, int32_t* file_index);
+int tsnap_load_job_add_member(tsnap_job* job, int32_t file_index, const tsnap_copy_desc* desc);
+/* the scatter kernels run on the engine's stream; `consumer_stream` (may be NULL) is made to wait
+ * for them before tsnap_job_wait returns. */
+int tsnap_load_job_submit(tsnap_job* job, void* consumer_stream);
+
+/* ---- stager/consumer seam for arbitrary StoragePlugins -----------------------------------------
+ * stage: pack members into ONE pinned host buffer and hand it out (BufferStager.stage_buffer ->
+ * memoryview, T:io_types.py:24-31).  The buffer stays valid until tsnap_buffer_release. */
+typedef struct tsnap_buffer tsnap_buffer;
+int tsnap_stage_submit(tsnap_engine* eng, const tsnap_copy_desc* members, int32_t n_members,
+                       uint64_t nbytes, void* producer_stream, tsnap_buffer** out);
+int tsnap_buffer_wait_device(tsnap_buffer* buf);
+int tsnap_buffer_wait(tsnap_buffer* buf, void** host_ptr, uint64_t* nbytes);
+int tsnap_buffer_release(tsnap_buffer* buf);
+/* consume: scatter a host byte buffer (what StoragePlugin.read produced) into destination views
+ * (BufferConsumer.consume_buffer, T:io_types.py:40-49).  Synchronous. */
+int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes,
+                  const tsnap_copy_desc* members, int32_t n_members, void* consumer_stream);
+
+/* ---- planning introspection (host only; used by the CPU test-suite) -----------------------------
+ * Normalises `members` exactly as a job would and reports the tile decomposition. */
+typedef struct tsnap_plan_info {
+    uint64_t n_members_bulk, n_members_lsu, n_members_host;
+    uint64_t n_tiles_bulk, n_tiles_lsu;
+    uint64_t bytes_bulk, bytes_lsu, bytes_host;
+} tsnap_plan_info;
+int tsnap_plan_describe(const tsnap_copy_desc* members, int32_t n_members, uint64_t wire_base_align,
+                        tsnap_plan_info* out);
+/* Executes the copies on the host with `threads` workers, wire side = wire_buf (host memory).  This is
+ * how HOST-space members (CPU tensors) are packed/unpacked; it shares the planner with the device path. */
+int tsnap_host_execute(const tsnap_copy_desc* members, int32_t n_members, void* wire_buf,
+                       uint64_t wire_nbytes, int32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSNAP_B200_H_ */

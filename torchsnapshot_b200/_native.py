@@ -1,0 +1,493 @@
+"""ctypes binding of ``libtsnap_b200.so`` (the C ABI declared in ``include/tsnap_b200.h``).
+
+The library is the product: there is no Python/PyTorch fallback for the device path.  If the shared
+object is missing this module raises at import time, and if the engine cannot get a usable sm_100
+device it raises at engine creation — loudly, never silently degrading to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtsnap_b200.so")
+
+MAX_DIMS = 8
+
+# enum tsnap_dtype
+U8, I8, I16, I32, I64, F16, BF16, F32, F64, BOOL = range(10)
+# enum tsnap_space
+SPACE_DEVICE, SPACE_HOST, SPACE_WIRE = 0, 1, 2
+
+ENGINE_NO_BULK = 1
+ENGINE_FSYNC = 2
+
+# the ten buffer-protocol dtypes of the reference (T:serialization.py:162-173)
+TORCH_TO_TSNAP = {
+    torch.uint8: U8,
+    torch.int8: I8,
+    torch.int16: I16,
+    torch.int32: I32,
+    torch.int64: I64,
+    torch.float16: F16,
+    torch.bfloat16: BF16,
+    torch.float32: F32,
+    torch.float64: F64,
+    torch.bool: BOOL,
+}
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str) -> None:
+        super().__init__(f"tsnap_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CopyDesc(C.Structure):
+    _fields_ = [
+        ("src_addr", C.c_uint64),
+        ("dst_addr", C.c_uint64),
+        ("sizes", C.c_int64 * MAX_DIMS),
+        ("src_strides", C.c_int64 * MAX_DIMS),
+        ("dst_strides", C.c_int64 * MAX_DIMS),
+        ("ndim", C.c_int32),
+        ("src_dtype", C.c_int32),
+        ("dst_dtype", C.c_int32),
+        ("src_space", C.c_int32),
+        ("dst_space", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class EngineConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32),
+        ("io_threads", C.c_int32),
+        ("pinned_slot_bytes", C.c_uint64),
+        ("pinned_slots", C.c_int32),
+        ("flags", C.c_int32),
+        ("hbm_staging_bytes", C.c_uint64),
+    ]
+
+
+class EngineStats(C.Structure):
+    _fields_ = [
+        ("pinned_bytes", C.c_uint64),
+        ("hbm_arena_bytes", C.c_uint64),
+        ("kernels_launched", C.c_uint64),
+        ("bytes_d2h", C.c_uint64),
+        ("bytes_h2d", C.c_uint64),
+        ("bytes_written", C.c_uint64),
+        ("bytes_read", C.c_uint64),
+        ("sm_count", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+class JobStats(C.Structure):
+    _fields_ = [
+        ("payload_bytes", C.c_uint64),
+        ("n_files", C.c_uint64),
+        ("n_members", C.c_uint64),
+        ("n_tiles_bulk", C.c_uint64),
+        ("n_tiles_lsu", C.c_uint64),
+        ("n_kernel_launches", C.c_uint64),
+        ("plan_ms", C.c_double),
+        ("kernel_ms", C.c_double),
+        ("kernel_bulk_ms", C.c_double),
+        ("kernel_lsu_ms", C.c_double),
+        ("device_done_ms", C.c_double),
+        ("total_ms", C.c_double),
+        ("table_h2d_bytes", C.c_uint64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("n_members_bulk", C.c_uint64),
+        ("n_members_lsu", C.c_uint64),
+        ("n_members_host", C.c_uint64),
+        ("n_tiles_bulk", C.c_uint64),
+        ("n_tiles_lsu", C.c_uint64),
+        ("bytes_bulk", C.c_uint64),
+        ("bytes_lsu", C.c_uint64),
+        ("bytes_host", C.c_uint64),
+    ]
+
+
+# every symbol include/tsnap_b200.h declares; tests assert the .so exports all of them
+EXPORTED_SYMBOLS = [
+    "tsnap_abi_version",
+    "tsnap_last_error",
+    "tsnap_dtype_size",
+    "tsnap_engine_create",
+    "tsnap_engine_destroy",
+    "tsnap_engine_trim",
+    "tsnap_engine_get_stats",
+    "tsnap_save_job_create",
+    "tsnap_save_job_add_file",
+    "tsnap_save_job_add_member",
+    "tsnap_save_job_submit",
+    "tsnap_job_wait_device",
+    "tsnap_job_wait",
+    "tsnap_job_done",
+    "tsnap_job_destroy",
+    "tsnap_job_get_stats",
+    "tsnap_load_job_create",
+    "tsnap_load_job_add_file",
+    "tsnap_load_job_add_member",
+    "tsnap_load_job_submit",
+    "tsnap_stage_submit",
+    "tsnap_buffer_wait_device",
+    "tsnap_buffer_wait",
+    "tsnap_buffer_release",
+    "tsnap_consume",
+    "tsnap_plan_describe",
+    "tsnap_host_execute",
+]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C torchsnapshot_b200/csrc`. torchsnapshot_b200 has no fallback data path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.tsnap_abi_version.restype = C.c_int
+    lib.tsnap_last_error.restype = C.c_char_p
+    lib.tsnap_dtype_size.restype = C.c_size_t
+    lib.tsnap_dtype_size.argtypes = [C.c_int]
+    lib.tsnap_engine_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(vp)]
+    lib.tsnap_engine_destroy.argtypes = [vp]
+    lib.tsnap_engine_trim.argtypes = [vp]
+    lib.tsnap_engine_get_stats.argtypes = [vp, C.POINTER(EngineStats)]
+    lib.tsnap_save_job_create.argtypes = [vp, C.POINTER(vp)]
+    lib.tsnap_load_job_create.argtypes = [vp, C.POINTER(vp)]
+    lib.tsnap_save_job_add_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(C.c_int32)]
+    lib.tsnap_load_job_add_file.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]
+    lib.tsnap_save_job_add_member.argtypes = [vp, C.c_int32, C.POINTER(CopyDesc)]
+    lib.tsnap_load_job_add_member.argtypes = [vp, C.c_int32, C.POINTER(CopyDesc)]
+    lib.tsnap_save_job_submit.argtypes = [vp, vp]
+    lib.tsnap_load_job_submit.argtypes = [vp, vp]
+    lib.tsnap_job_wait_device.argtypes = [vp]
+    lib.tsnap_job_wait.argtypes = [vp]
+    lib.tsnap_job_done.argtypes = [vp]
+    lib.tsnap_job_destroy.argtypes = [vp]
+    lib.tsnap_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
+    lib.tsnap_stage_submit.argtypes = [vp, C.POINTER(CopyDesc), C.c_int32, C.c_uint64, vp, C.POINTER(vp)]
+    lib.tsnap_buffer_wait_device.argtypes = [vp]
+    lib.tsnap_buffer_wait.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    lib.tsnap_buffer_release.argtypes = [vp]
+    lib.tsnap_consume.argtypes = [vp, vp, C.c_uint64, C.POINTER(CopyDesc), C.c_int32, vp]
+    lib.tsnap_plan_describe.argtypes = [C.POINTER(CopyDesc), C.c_int32, C.c_uint64, C.POINTER(PlanInfo)]
+    lib.tsnap_host_execute.argtypes = [C.POINTER(CopyDesc), C.c_int32, vp, C.c_uint64, C.c_int32]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("tsnap_last_error", "tsnap_dtype_size"):
+            fn.restype = C.c_int
+    if lib.tsnap_abi_version() != 1:
+        raise ImportError("libtsnap_b200.so ABI version mismatch; rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise NativeError(rc, (lib.tsnap_last_error() or b"").decode("utf-8", "replace"))
+
+
+def tsnap_dtype(dtype: torch.dtype) -> int:
+    try:
+        return TORCH_TO_TSNAP[dtype]
+    except KeyError:
+        raise NativeError(-6, f"dtype {dtype} has no raw wire format (not a buffer-protocol dtype)") from None
+
+
+def _space_of(t: torch.Tensor) -> int:
+    if t.is_cuda:
+        return SPACE_DEVICE
+    if t.device.type == "cpu":
+        return SPACE_HOST
+    raise NativeError(-6, f"tensors on {t.device} are not supported")
+
+
+def _fill_view(d: CopyDesc, t: torch.Tensor) -> None:
+    if t.dim() > MAX_DIMS:
+        raise NativeError(-6, f"tensors with more than {MAX_DIMS} dims are not supported")
+    d.ndim = t.dim()
+    for i, s in enumerate(t.shape):
+        d.sizes[i] = s
+
+
+def save_desc(t: torch.Tensor, wire_offset: int, wire_dtype: Optional[torch.dtype] = None) -> CopyDesc:
+    """tensor view -> wire image at ``wire_offset`` (C-contiguous layout of ``t.shape``)."""
+    d = CopyDesc()
+    _fill_view(d, t)
+    for i, s in enumerate(t.stride()):
+        d.src_strides[i] = s
+    d.src_addr = t.data_ptr()
+    d.dst_addr = wire_offset
+    d.src_dtype = tsnap_dtype(t.dtype)
+    d.dst_dtype = tsnap_dtype(wire_dtype or t.dtype)
+    d.src_space = _space_of(t)
+    d.dst_space = SPACE_WIRE
+    return d
+
+
+def load_desc(
+    t: torch.Tensor,
+    wire_offset: int,
+    wire_dtype: Optional[torch.dtype] = None,
+    wire_strides: Optional[Sequence[int]] = None,
+) -> CopyDesc:
+    """wire bytes at ``wire_offset`` -> tensor view.  ``wire_strides`` (elements) describe the saved
+    piece when ``t`` receives a sub-box of it (reshard-on-load); default: the piece has ``t``'s shape."""
+    d = CopyDesc()
+    _fill_view(d, t)
+    if wire_strides is None:
+        acc = 1
+        ws = [0] * t.dim()
+        for i in range(t.dim() - 1, -1, -1):
+            ws[i] = acc
+            acc *= t.shape[i]
+        wire_strides = ws
+    for i, s in enumerate(wire_strides):
+        d.src_strides[i] = s
+    for i, s in enumerate(t.stride()):
+        d.dst_strides[i] = s
+    d.src_addr = wire_offset
+    d.dst_addr = t.data_ptr()
+    d.src_dtype = tsnap_dtype(wire_dtype or t.dtype)
+    d.dst_dtype = tsnap_dtype(t.dtype)
+    d.src_space = SPACE_WIRE
+    d.dst_space = _space_of(t)
+    return d
+
+
+def _desc_array(descs: Sequence[CopyDesc]):
+    arr = (CopyDesc * max(1, len(descs)))()
+    for i, d in enumerate(descs):
+        arr[i] = d
+    return arr
+
+
+class Job:
+    """A save or load job.  Keeps the tensors it references alive until it is destroyed."""
+
+    def __init__(self, engine: "Engine", handle: C.c_void_p, save: bool) -> None:
+        self.engine = engine
+        self._h = handle
+        self._save = save
+        self._keepalive: List[object] = []
+        self._destroyed = False
+
+    def add_file(self, path: str, nbytes: int, offset: int = 0) -> int:
+        idx = C.c_int32(-1)
+        if self._save:
+            check(lib.tsnap_save_job_add_file(self._h, os.fsencode(path), nbytes, C.byref(idx)))
+        else:
+            check(lib.tsnap_load_job_add_file(self._h, os.fsencode(path), offset, nbytes, C.byref(idx)))
+        return idx.value
+
+    def add_member(self, file_index: int, desc: CopyDesc, keepalive: object = None) -> None:
+        fn = lib.tsnap_save_job_add_member if self._save else lib.tsnap_load_job_add_member
+        check(fn(self._h, file_index, C.byref(desc)))
+        if keepalive is not None:
+            self._keepalive.append(keepalive)
+
+    def submit(self, stream: Optional[int] = None) -> None:
+        fn = lib.tsnap_save_job_submit if self._save else lib.tsnap_load_job_submit
+        check(fn(self._h, C.c_void_p(stream or 0)))
+
+    def wait_device(self) -> None:
+        check(lib.tsnap_job_wait_device(self._h))
+
+    def wait(self) -> None:
+        check(lib.tsnap_job_wait(self._h))
+
+    def done(self) -> bool:
+        return bool(lib.tsnap_job_done(self._h))
+
+    def stats(self) -> dict:
+        st = JobStats()
+        check(lib.tsnap_job_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def destroy(self) -> None:
+        if not self._destroyed:
+            self._destroyed = True
+            lib.tsnap_job_destroy(self._h)
+            self._keepalive.clear()
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class StagedBuffer:
+    """Pinned host buffer produced by the stager seam; exposes the buffer protocol via memoryview."""
+
+    def __init__(self, engine: "Engine", handle: C.c_void_p, nbytes: int, keepalive: List[object]) -> None:
+        self.engine = engine
+        self._h = handle
+        self.nbytes = nbytes
+        self._keepalive = keepalive
+        self._released = False
+
+    def wait_device(self) -> None:
+        check(lib.tsnap_buffer_wait_device(self._h))
+
+    def wait(self) -> memoryview:
+        ptr = C.c_void_p()
+        n = C.c_uint64()
+        check(lib.tsnap_buffer_wait(self._h, C.byref(ptr), C.byref(n)))
+        if n.value == 0:
+            return memoryview(b"")
+        arr = (C.c_char * n.value).from_address(ptr.value)
+        # the memoryview keeps `arr` alive, `arr._owner` keeps this object (and the pinned block) alive
+        arr._owner = self
+        return memoryview(arr).cast("B")
+
+    def release(self) -> None:
+        if not self._released:
+            self._released = True
+            lib.tsnap_buffer_release(self._h)
+            self._keepalive = []
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(
+        self,
+        device: int = -1,
+        io_threads: int = 0,
+        pinned_slot_bytes: int = 0,
+        pinned_slots: int = 0,
+        flags: int = 0,
+        hbm_staging_bytes: int = 0,
+    ) -> None:
+        cfg = EngineConfig(device, io_threads, pinned_slot_bytes, pinned_slots, flags, hbm_staging_bytes)
+        h = C.c_void_p()
+        check(lib.tsnap_engine_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.device = device
+        self._closed = False
+
+    def save_job(self) -> Job:
+        h = C.c_void_p()
+        check(lib.tsnap_save_job_create(self._h, C.byref(h)))
+        return Job(self, h, True)
+
+    def load_job(self) -> Job:
+        h = C.c_void_p()
+        check(lib.tsnap_load_job_create(self._h, C.byref(h)))
+        return Job(self, h, False)
+
+    def stage(self, descs: Sequence[CopyDesc], nbytes: int, stream: Optional[int] = None, keepalive=None) -> StagedBuffer:
+        arr = _desc_array(descs)
+        h = C.c_void_p()
+        check(lib.tsnap_stage_submit(self._h, arr, len(descs), nbytes, C.c_void_p(stream or 0), C.byref(h)))
+        return StagedBuffer(self, h, nbytes, list(keepalive or []))
+
+    def consume(self, buf, descs: Sequence[CopyDesc]) -> None:
+        mv = memoryview(buf).cast("B")
+        n = mv.nbytes
+        if n == 0:
+            return
+        if mv.readonly:
+            # ctypes cannot borrow a read-only buffer without a copy unless we go through its address
+            import numpy as np
+
+            addr = np.frombuffer(mv, dtype=np.uint8).__array_interface__["data"][0]
+        else:
+            addr = C.addressof(C.c_char.from_buffer(mv))
+        arr = _desc_array(descs)
+        check(lib.tsnap_consume(self._h, C.c_void_p(addr), n, arr, len(descs), None))
+
+    def stats(self) -> dict:
+        st = EngineStats()
+        check(lib.tsnap_engine_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def trim(self) -> None:
+        check(lib.tsnap_engine_trim(self._h))
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            lib.tsnap_engine_destroy(self._h)
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_execute(descs: Sequence[CopyDesc], wire: "torch.Tensor | bytearray | memoryview", threads: int = 1) -> None:
+    """HOST<->WIRE copies against a host wire buffer (shares the planner with the device path)."""
+    if isinstance(wire, torch.Tensor):
+        addr, n = wire.data_ptr(), wire.numel() * wire.element_size()
+    else:
+        mv = memoryview(wire).cast("B")
+        n = mv.nbytes
+        addr = C.addressof(C.c_char.from_buffer(mv)) if n else 0
+    arr = _desc_array(descs)
+    check(lib.tsnap_host_execute(arr, len(descs), C.c_void_p(addr), n, threads))
+
+
+def plan_describe(descs: Sequence[CopyDesc], wire_base_align: int = 0) -> dict:
+    info = PlanInfo()
+    arr = _desc_array(descs)
+    check(lib.tsnap_plan_describe(arr, len(descs), wire_base_align, C.byref(info)))
+    return {k: getattr(info, k) for k, _ in info._fields_}
+
+
+# ---- process-wide engines -----------------------------------------------------------------------
+_engines: dict = {}
+_engines_lock = threading.Lock()
+
+
+def get_engine(device: int = -1, **kwargs) -> Engine:
+    """One engine per device per process (the pinned ring costs ~0.5 s/GiB to create, so it is kept)."""
+    with _engines_lock:
+        key = device
+        eng = _engines.get(key)
+        if eng is None:
+            env = os.environ
+            opts = dict(
+                io_threads=int(env.get("TSNAP_B200_IO_THREADS", "0")),
+                pinned_slot_bytes=int(env.get("TSNAP_B200_PINNED_SLOT_BYTES", "0")),
+                pinned_slots=int(env.get("TSNAP_B200_PINNED_SLOTS", "0")),
+                flags=int(env.get("TSNAP_B200_ENGINE_FLAGS", "0")),
+                hbm_staging_bytes=int(env.get("TSNAP_B200_HBM_STAGING_BYTES", "0")),
+            )
+            opts.update(kwargs)
+            eng = Engine(device=device, **opts)
+            _engines[key] = eng
+        return eng
+
+
+def reset_engines() -> None:
+    with _engines_lock:
+        for eng in _engines.values():
+            eng.close()
+        _engines.clear()

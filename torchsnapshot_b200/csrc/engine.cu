@@ -1,0 +1,1379 @@
+// Host side of the data plane: engine, jobs and the C ABI (include/tsnap_b200.h).
+//
+// Save pipeline (one job = the raw-tensor WriteReqs of one Snapshot.take on this rank):
+//
+//   live tensors --pack kernels--> HBM staging arena --cudaMemcpyAsync(s_copy)--> pinned slot ring
+//        (s_kernel, ~TB/s)              |  async_take returns here                  | completion thread
+//                                        v                                           v
+//                                  sources reusable                     I/O workers: pwrite(fd, slot, off)
+//
+// Load pipeline is the mirror: I/O workers pread into pinned slots, enqueue the H2D copy into the
+// arena themselves, and the worker that uploads the last chunk of a wave launches the scatter
+// kernels that write straight into the live (possibly strided / resharded) tensors.
+//
+// This replaces, for the requests it is handed, the asyncio state machine + ThreadPoolExecutor(4)
+// of T:scheduler.py:222-339/386-446, the pageable `tensor.to("cpu")` of T:io_preparers/tensor.py:353,
+// the per-member D2D copies + blocking `.cpu()` of T:batcher.py:144-159 and the aiofiles hop of
+// T:storage_plugins/fs.py:28-51.
+#include "engine.h"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "kernels.h"
+
+namespace tsnap {
+
+static thread_local std::string g_err;
+int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+const char* last_err() { return g_err.c_str(); }
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return set_err(TSNAP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+using clk = std::chrono::steady_clock;
+static double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
+
+// ---- WorkerPool ---------------------------------------------------------------------------------------
+WorkerPool::WorkerPool(int n) {
+    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { run(); });
+}
+WorkerPool::~WorkerPool() {
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+}
+void WorkerPool::post(std::function<void()> fn) {
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        q_.push_back(std::move(fn));
+    }
+    cv_.notify_one();
+}
+void WorkerPool::run() {
+    for (;;) {
+        std::function<void()> fn;
+        {
+            std::unique_lock<std::mutex> g(mu_);
+            cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+            if (q_.empty()) return;
+            fn = std::move(q_.front());
+            q_.pop_front();
+        }
+        fn();
+    }
+}
+
+// ---- SlotRing -------------------------------------------------------------------------------------------
+int SlotRing::init(size_t slot_bytes, int n, bool pinned) {
+    slot_bytes_ = slot_bytes;
+    pinned_ = pinned;
+    for (int i = 0; i < n; ++i) {
+        void* p = nullptr;
+        if (pinned) {
+            cudaError_t e = cudaHostAlloc(&p, slot_bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) return set_err(TSNAP_ECUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        } else {
+            if (posix_memalign(&p, 4096, slot_bytes) != 0) return set_err(TSNAP_ENOMEM, "posix_memalign failed");
+        }
+        all_.push_back(static_cast<char*>(p));
+        free_.push_back(static_cast<char*>(p));
+    }
+    return TSNAP_OK;
+}
+void SlotRing::destroy() {
+    for (char* p : all_) {
+        if (pinned_) cudaFreeHost(p);
+        else free(p);
+    }
+    all_.clear();
+    free_.clear();
+}
+char* SlotRing::acquire() {
+    std::unique_lock<std::mutex> g(mu_);
+    cv_.wait(g, [this] { return !free_.empty(); });
+    char* p = free_.back();
+    free_.pop_back();
+    return p;
+}
+void SlotRing::release(char* p) {
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        free_.push_back(p);
+    }
+    cv_.notify_one();
+}
+
+// ---- small file helpers -----------------------------------------------------------------------------------
+static int make_parent_dirs(const std::string& path) {
+    size_t pos = path.rfind('/');
+    if (pos == std::string::npos || pos == 0) return 0;
+    std::string dir = path.substr(0, pos);
+    struct stat st;
+    if (stat(dir.c_str(), &st) == 0) return 0;
+    for (size_t i = 1; i <= dir.size(); ++i) {
+        if (i == dir.size() || dir[i] == '/') {
+            std::string sub = dir.substr(0, i);
+            if (mkdir(sub.c_str(), 0777) != 0 && errno != EEXIST) return -1;
+        }
+    }
+    return 0;
+}
+static int pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
+    while (n > 0) {
+        ssize_t w = pwrite(fd, p, n, off_t(off));
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        p += w;
+        n -= size_t(w);
+        off += uint64_t(w);
+    }
+    return 0;
+}
+static int pread_all(int fd, char* p, size_t n, uint64_t off) {
+    while (n > 0) {
+        ssize_t r = pread(fd, p, n, off_t(off));
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        if (r == 0) {
+            errno = ENODATA;  // short file
+            return -1;
+        }
+        p += r;
+        n -= size_t(r);
+        off += uint64_t(r);
+    }
+    return 0;
+}
+
+static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace tsnap
+
+using namespace tsnap;
+
+// ---- job plumbing -----------------------------------------------------------------------------------------
+void tsnap_job::fail(int code, const std::string& msg) {
+    std::lock_guard<std::mutex> g(mu);
+    if (err_code == 0) {
+        err_code = code;
+        err_msg = msg;
+    }
+}
+bool tsnap_job::failed() {
+    std::lock_guard<std::mutex> g(mu);
+    return err_code != 0;
+}
+void tsnap_job::part_done() {
+    if (parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> g(mu);
+        stats.total_ms = ms_since(t_submit);
+        if (!device_done) {
+            device_done = true;
+            stats.device_done_ms = stats.total_ms;
+        }
+        done = true;
+        cv.notify_all();
+    }
+}
+
+cudaEvent_t tsnap_engine::get_event() {
+    {
+        std::lock_guard<std::mutex> g(ev_mu);
+        if (!ev_free.empty()) {
+            cudaEvent_t e = ev_free.back();
+            ev_free.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+void tsnap_engine::put_event(cudaEvent_t e) {
+    std::lock_guard<std::mutex> g(ev_mu);
+    ev_free.push_back(e);
+}
+
+static void push_pending(tsnap_engine* eng, cudaEvent_t ev, std::function<void(bool)> fn) {
+    {
+        std::lock_guard<std::mutex> g(eng->c_mu);
+        eng->pending.push_back({ev, std::move(fn)});
+    }
+    eng->c_cv.notify_one();
+}
+
+static void completion_main(tsnap_engine* eng) {
+    cudaSetDevice(eng->device);
+    for (;;) {
+        tsnap_engine::Pending p;
+        {
+            std::unique_lock<std::mutex> g(eng->c_mu);
+            eng->c_cv.wait(g, [eng] { return eng->stopping || !eng->pending.empty(); });
+            if (eng->pending.empty()) return;
+            p = std::move(eng->pending.front());
+            eng->pending.pop_front();
+        }
+        cudaError_t e = cudaEventSynchronize(p.ev);
+        p.done(e == cudaSuccess);
+    }
+}
+
+// ---- planning of one wave ----------------------------------------------------------------------------------
+static int plan_wave(tsnap_job* job, Wave& w, bool wire_is_dst) {
+    tsnap_engine* eng = job->eng;
+    std::string err;
+    for (int fi : w.files) {
+        FileSpec& f = job->files[fi];
+        const uint64_t wire_base = uint64_t(uintptr_t(eng->arena)) + w.region_off + f.arena_off;
+        for (const tsnap_copy_desc& d : f.members) {
+            NormalizedCopy nc;
+            int rc = normalize_copy(d, wire_base, eng->allow_bulk, &nc, &err);
+            if (rc != TSNAP_OK) return set_err(rc, "member of " + f.path + ": " + err);
+            (void)wire_is_dst;
+            for (int k = 0; k < nc.n; ++k) {
+                const Member& m = nc.m[k];
+                const uint64_t nt = tile_count(m);
+                if (nt == 0) continue;
+                const uint32_t mi = uint32_t(w.members.size());
+                w.members.push_back(m);
+                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : w.tiles_lsu;
+                for (uint64_t t = 0; t < nt; ++t) tv.push_back(Tile{mi, uint32_t(t)});
+            }
+        }
+    }
+    job->stats.n_tiles_bulk += w.tiles_bulk.size();
+    job->stats.n_tiles_lsu += w.tiles_lsu.size();
+    return TSNAP_OK;
+}
+
+// copies the tables to the device and launches both kernels on s_kernel; records timing events
+static int launch_wave(tsnap_job* job, Wave& w) {
+    tsnap_engine* eng = job->eng;
+    const size_t mb = w.members.size() * sizeof(Member);
+    const size_t bb = w.tiles_bulk.size() * sizeof(Tile);
+    const size_t lb = w.tiles_lsu.size() * sizeof(Tile);
+    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(lb, 256);
+    CUDA_TRY(cudaEventCreate(&w.ev_k0));
+    CUDA_TRY(cudaEventCreate(&w.ev_k1));
+    CUDA_TRY(cudaEventCreate(&w.ev_k2));
+    CUDA_TRY(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
+    if (w.members.empty()) {
+        CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
+        CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
+        CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
+        CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
+        return TSNAP_OK;
+    }
+    CUDA_TRY(cudaMallocAsync(&w.d_tables, w.table_bytes, eng->s_kernel));
+    char* d = static_cast<char*>(w.d_tables);
+    Member* d_members = reinterpret_cast<Member*>(d);
+    Tile* d_bulk = reinterpret_cast<Tile*>(d + align_up(mb, 256));
+    Tile* d_lsu = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256));
+    // pageable sources: the runtime stages them before returning, so the vectors may be freed later
+    CUDA_TRY(cudaMemcpyAsync(d_members, w.members.data(), mb, cudaMemcpyHostToDevice, eng->s_kernel));
+    if (bb) CUDA_TRY(cudaMemcpyAsync(d_bulk, w.tiles_bulk.data(), bb, cudaMemcpyHostToDevice, eng->s_kernel));
+    if (lb) CUDA_TRY(cudaMemcpyAsync(d_lsu, w.tiles_lsu.data(), lb, cudaMemcpyHostToDevice, eng->s_kernel));
+    job->stats.table_h2d_bytes += mb + bb + lb;
+    CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
+    CUDA_TRY(launch_bulk(d_members, d_bulk, uint32_t(w.tiles_bulk.size()), eng->sm_count, eng->s_kernel));
+    CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
+    CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel));
+    CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
+    CUDA_TRY(cudaFreeAsync(w.d_tables, eng->s_kernel));
+    CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
+    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1);
+    job->stats.n_kernel_launches += nl;
+    eng->kernels_launched += nl;
+    return TSNAP_OK;
+}
+
+static void collect_wave_timing(tsnap_job* job, Wave& w) {
+    float a = 0, b = 0;
+    if (w.ev_k0 && cudaEventElapsedTime(&a, w.ev_k0, w.ev_k1) == cudaSuccess &&
+        cudaEventElapsedTime(&b, w.ev_k1, w.ev_k2) == cudaSuccess) {
+        std::lock_guard<std::mutex> g(job->mu);
+        job->stats.kernel_bulk_ms += a;
+        job->stats.kernel_lsu_ms += b;
+        job->stats.kernel_ms += a + b;
+    }
+}
+
+static int ensure_arena(tsnap_engine* eng, uint64_t need, uint64_t largest_file) {
+    if (need <= eng->arena_bytes) return TSNAP_OK;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t reserve = std::max<uint64_t>(total_b / 8, 4ull << 30);
+    uint64_t allowed = eng->arena_bytes + (free_b > reserve ? free_b - reserve : 0);
+    if (eng->cfg.hbm_staging_bytes) allowed = std::min<uint64_t>(allowed, eng->cfg.hbm_staging_bytes);
+    uint64_t target = std::min(need, allowed);
+    if (target < need) {
+        // multi-wave mode needs two half-arenas that each hold the largest file
+        const uint64_t min_two = 2 * align_up(largest_file, 256);
+        if (target < min_two) target = min_two;
+        if (target > eng->arena_bytes + free_b)
+            return set_err(TSNAP_ECUDA, "not enough free HBM for the staging arena");
+    }
+    target = align_up(target, 2ull << 20);
+    if (target <= eng->arena_bytes) return TSNAP_OK;
+    if (eng->arena) {
+        CUDA_TRY(cudaStreamSynchronize(eng->s_kernel));
+        CUDA_TRY(cudaStreamSynchronize(eng->s_copy));
+        CUDA_TRY(cudaFree(eng->arena));
+        eng->arena = nullptr;
+        eng->arena_bytes = 0;
+    }
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, target));
+    eng->arena = static_cast<char*>(p);
+    eng->arena_bytes = target;
+    return TSNAP_OK;
+}
+
+static int ensure_ring(tsnap_engine* eng) {
+    if (eng->ring.total_bytes() > 0) return TSNAP_OK;
+    const size_t sb = eng->cfg.pinned_slot_bytes ? eng->cfg.pinned_slot_bytes : (32ull << 20);
+    const int n = eng->cfg.pinned_slots ? eng->cfg.pinned_slots : 32;
+    return eng->ring.init(sb, n, eng->has_device);
+}
+
+// groups the device files of a job into waves that fit the arena
+static int build_waves(tsnap_job* job) {
+    tsnap_engine* eng = job->eng;
+    uint64_t total = 0, largest = 0;
+    std::vector<int> dev_files;
+    for (size_t i = 0; i < job->files.size(); ++i) {
+        FileSpec& f = job->files[i];
+        if (f.host_only || f.nbytes == 0) continue;
+        dev_files.push_back(int(i));
+        total += align_up(f.nbytes, 256);
+        largest = std::max(largest, f.nbytes);
+    }
+    if (dev_files.empty()) return TSNAP_OK;
+    if (!eng->has_device) return set_err(TSNAP_ECUDA, "job has device members but the engine is host-only");
+    int rc = ensure_arena(eng, total, largest);
+    if (rc != TSNAP_OK) return rc;
+    const bool single = total <= eng->arena_bytes;
+    const uint64_t cap = single ? eng->arena_bytes : (eng->arena_bytes / 2) / 256 * 256;
+    job->waves.emplace_back();
+    for (int fi : dev_files) {
+        FileSpec& f = job->files[fi];
+        const uint64_t fb = align_up(f.nbytes, 256);
+        if (fb > cap) return set_err(TSNAP_ECUDA, "file larger than half of the staging arena: " + f.path);
+        if (job->waves.back().bytes + fb > cap) job->waves.emplace_back();
+        Wave& w = job->waves.back();
+        f.arena_off = w.bytes;
+        f.wave = int(job->waves.size()) - 1;
+        w.bytes += fb;
+        w.files.push_back(fi);
+    }
+    for (size_t i = 0; i < job->waves.size(); ++i) job->waves[i].region_off = single ? 0 : (i % 2) * cap;
+    return TSNAP_OK;
+}
+
+// ---- host-only files -----------------------------------------------------------------------------------
+// true when the file is exactly one dense, cast-free member that covers it: I/O goes straight
+// from/to the tensor's own memory (the reference's zero-copy tensor_as_memoryview, T:serialization.py:177-204)
+static bool direct_host_member(const FileSpec& f, bool save, Member* out) {
+    if (f.members.size() != 1) return false;
+    NormalizedCopy nc;
+    std::string err;
+    if (normalize_copy(f.members[0], 0, false, &nc, &err) != TSNAP_OK || nc.n != 1) return false;
+    const Member& m = nc.m[0];
+    if (m.mode != kModeContig || m.bytes != f.nbytes) return false;
+    if ((save ? m.dst : m.src) != 0) return false;
+    *out = m;
+    return true;
+}
+
+static void finish_file_part(tsnap_job* job, FileSpec& f, uint64_t bytes_io, bool save) {
+    if (save) job->eng->bytes_written += bytes_io;
+    else job->eng->bytes_read += bytes_io;
+    if (f.parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1 && f.fd >= 0) {
+        if (save && (job->eng->cfg.flags & TSNAP_ENGINE_FSYNC)) fsync(f.fd);
+        close(f.fd);
+        f.fd = -1;
+    }
+    job->part_done();
+}
+
+static int open_file(tsnap_job* job, FileSpec& f, bool save) {
+    if (save) {
+        if (make_parent_dirs(f.path) != 0) return set_err(TSNAP_EIO, "mkdir for " + f.path + ": " + strerror(errno));
+        f.fd = open(f.path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    } else {
+        f.fd = open(f.path.c_str(), O_RDONLY);
+    }
+    if (f.fd < 0) return set_err(TSNAP_EIO, "open " + f.path + ": " + strerror(errno));
+    (void)job;
+    return TSNAP_OK;
+}
+
+// number of I/O parts a file contributes
+static int64_t count_parts(tsnap_engine* eng, const FileSpec& f, bool save) {
+    if (f.nbytes == 0) return save ? 1 : 0;  // an empty file still has to be created on save
+    const uint64_t sb = eng->ring.slot_bytes();
+    if (f.host_only) {
+        Member m;
+        if (direct_host_member(f, save, &m)) return int64_t((f.nbytes + sb - 1) / sb);
+        return 1;
+    }
+    return int64_t((f.nbytes + sb - 1) / sb);
+}
+
+static void post_host_file(tsnap_job* job, int fi, bool save) {
+    tsnap_engine* eng = job->eng;
+    FileSpec& f = job->files[fi];
+    const uint64_t sb = eng->ring.slot_bytes();
+    if (f.nbytes == 0) {
+        if (save) eng->io->post([job, &f] { finish_file_part(job, f, 0, true); });
+        return;
+    }
+    Member dm;
+    if (direct_host_member(f, save, &dm)) {
+        for (uint64_t lo = 0; lo < f.nbytes; lo += sb) {
+            const uint64_t n = std::min(sb, f.nbytes - lo);
+            eng->io->post([job, &f, dm, lo, n, save] {
+                if (!job->failed()) {
+                    int rc = save ? pwrite_all(f.fd, reinterpret_cast<const char*>(uintptr_t(dm.src)) + lo, n, lo)
+                                  : pread_all(f.fd, reinterpret_cast<char*>(uintptr_t(dm.dst)) + lo, n, f.offset + lo);
+                    if (rc != 0) job->fail(TSNAP_EIO, (save ? "pwrite " : "pread ") + f.path + ": " + strerror(errno));
+                }
+                finish_file_part(job, f, n, save);
+            });
+        }
+        return;
+    }
+    eng->io->post([job, &f, save] {
+        if (!job->failed()) {
+            char* tmp = static_cast<char*>(malloc(f.nbytes));
+            if (!tmp) {
+                job->fail(TSNAP_ENOMEM, "malloc of a host slab failed");
+            } else {
+                std::string err;
+                bool ok = true;
+                if (!save && pread_all(f.fd, tmp, f.nbytes, f.offset) != 0) {
+                    job->fail(TSNAP_EIO, "pread " + f.path + ": " + strerror(errno));
+                    ok = false;
+                }
+                for (size_t i = 0; ok && i < f.members.size(); ++i) {
+                    NormalizedCopy nc;
+                    int rc = normalize_copy(f.members[i], uint64_t(uintptr_t(tmp)), false, &nc, &err);
+                    if (rc != TSNAP_OK) {
+                        job->fail(rc, "member of " + f.path + ": " + err);
+                        ok = false;
+                        break;
+                    }
+                    for (int k = 0; k < nc.n; ++k) host_copy_range(nc.m[k], 0, nc.m[k].bytes);
+                }
+                if (ok && save && pwrite_all(f.fd, tmp, f.nbytes, 0) != 0)
+                    job->fail(TSNAP_EIO, "pwrite " + f.path + ": " + strerror(errno));
+                free(tmp);
+            }
+        }
+        finish_file_part(job, f, f.nbytes, save);
+    });
+}
+
+// ---- save ------------------------------------------------------------------------------------------------
+static void mark_device_done(tsnap_job* job) {
+    std::lock_guard<std::mutex> g(job->mu);
+    if (!job->device_done) {
+        job->device_done = true;
+        job->stats.device_done_ms = ms_since(job->t_submit);
+        job->cv.notify_all();
+    }
+}
+
+static void finish_job_now(tsnap_job* job) {
+    // used when nothing asynchronous is outstanding
+    job->parts_left.store(1);
+    job->part_done();
+}
+
+static int run_save_inner(tsnap_job* job) {
+    tsnap_engine* eng = job->eng;
+    int rc = ensure_ring(eng);
+    if (rc != TSNAP_OK) return rc;
+    auto t0 = clk::now();
+    rc = build_waves(job);
+    if (rc != TSNAP_OK) return rc;
+    for (Wave& w : job->waves) {
+        rc = plan_wave(job, w, true);
+        if (rc != TSNAP_OK) return rc;
+    }
+    job->stats.plan_ms = ms_since(t0);
+    // open every file first and compute the part count before anything can complete
+    int64_t parts = 0;
+    for (FileSpec& f : job->files) {
+        rc = open_file(job, f, true);
+        if (rc != TSNAP_OK) return rc;
+        const int64_t p = count_parts(eng, f, true);
+        f.parts_left.store(p);
+        parts += p;
+    }
+    if (parts == 0) {
+        mark_device_done(job);
+        finish_job_now(job);
+        return TSNAP_OK;
+    }
+    for (Wave& w : job->waves) CUDA_TRY(cudaEventCreateWithFlags(&w.ev_copied, cudaEventDisableTiming));
+    job->parts_left.store(parts);
+    if (job->waves.empty()) mark_device_done(job);
+
+    const size_t nw = job->waves.size();
+    size_t launched = 0;
+    auto launch_next = [&]() -> int {
+        Wave& w = job->waves[launched];
+        if (launched >= 2) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->waves[launched - 2].ev_copied, 0));
+        if (launched == 0 && job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
+        int r = launch_wave(job, w);
+        if (r != TSNAP_OK) return r;
+        ++launched;
+        if (launched == nw) {
+            Wave* last = &w;
+            push_pending(eng, w.ev_done, [job, last](bool ok) {
+                if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
+                (void)last;
+                mark_device_done(job);
+            });
+        }
+        return TSNAP_OK;
+    };
+    // the device pipeline may be aborted half-way; account for the parts that will never be posted
+    int64_t posted_parts = 0;
+    auto abort_rest = [&](int64_t total_parts) {
+        for (int64_t i = posted_parts; i < total_parts; ++i) job->part_done();
+    };
+    // host-only files go straight to the I/O workers
+    for (size_t i = 0; i < job->files.size(); ++i) {
+        FileSpec& f = job->files[i];
+        if (f.host_only || f.nbytes == 0) {
+            posted_parts += f.parts_left.load();
+            post_host_file(job, int(i), true);
+        }
+    }
+    for (size_t k = 0; k < std::min<size_t>(2, nw); ++k) {
+        rc = launch_next();
+        if (rc != TSNAP_OK) {
+            job->fail(rc, last_err());
+            mark_device_done(job);
+            abort_rest(parts);
+            return TSNAP_OK;
+        }
+    }
+    const uint64_t sb = eng->ring.slot_bytes();
+    for (size_t wi = 0; wi < nw; ++wi) {
+        Wave& w = job->waves[wi];
+        bool ok = cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0) == cudaSuccess;
+        for (int fi : w.files) {
+            FileSpec& f = job->files[fi];
+            const char* base = eng->arena + w.region_off + f.arena_off;
+            for (uint64_t lo = 0; lo < f.nbytes; lo += sb) {
+                const uint64_t n = std::min(sb, f.nbytes - lo);
+                char* slot = eng->ring.acquire();
+                cudaEvent_t ev = eng->get_event();
+                ok = ok && !job->failed() &&
+                     cudaMemcpyAsync(slot, base + lo, n, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess &&
+                     cudaEventRecord(ev, eng->s_copy) == cudaSuccess;
+                if (!ok) job->fail(TSNAP_ECUDA, std::string("D2H copy: ") + cudaGetErrorString(cudaGetLastError()));
+                eng->bytes_d2h += n;
+                ++posted_parts;
+                FileSpec* fp = &f;
+                push_pending(eng, ev, [eng, job, fp, slot, lo, n, ev](bool evok) {
+                    eng->put_event(ev);
+                    if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
+                    eng->io->post([eng, job, fp, slot, lo, n] {
+                        if (!job->failed() && pwrite_all(fp->fd, slot, n, lo) != 0)
+                            job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
+                        eng->ring.release(slot);
+                        finish_file_part(job, *fp, n, true);
+                    });
+                });
+            }
+        }
+        if (cudaEventRecord(w.ev_copied, eng->s_copy) != cudaSuccess) job->fail(TSNAP_ECUDA, "event record failed");
+        if (launched < nw) {
+            rc = launch_next();
+            if (rc != TSNAP_OK) {
+                job->fail(rc, last_err());
+                mark_device_done(job);
+                // remaining waves are never issued
+                int64_t remaining = 0;
+                for (size_t wj = wi + 1; wj < nw; ++wj)
+                    for (int fj : job->waves[wj].files) remaining += job->files[fj].parts_left.load();
+                for (int64_t i = 0; i < remaining; ++i) job->part_done();
+                return TSNAP_OK;
+            }
+        }
+    }
+    return TSNAP_OK;
+}
+
+// ---- load ------------------------------------------------------------------------------------------------
+struct LoadShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> launched;  // per wave: scatter kernels enqueued
+};
+
+static int run_load_inner(tsnap_job* job) {
+    tsnap_engine* eng = job->eng;
+    int rc = ensure_ring(eng);
+    if (rc != TSNAP_OK) return rc;
+    auto t0 = clk::now();
+    rc = build_waves(job);
+    if (rc != TSNAP_OK) return rc;
+    for (Wave& w : job->waves) {
+        rc = plan_wave(job, w, false);
+        if (rc != TSNAP_OK) return rc;
+    }
+    job->stats.plan_ms = ms_since(t0);
+    const uint64_t sb = eng->ring.slot_bytes();
+    int64_t parts = 0;
+    for (FileSpec& f : job->files) {
+        if (f.nbytes == 0) continue;
+        if (!f.mem_src) {
+            rc = open_file(job, f, false);
+            if (rc != TSNAP_OK) return rc;
+        }
+        const int64_t p = count_parts(eng, f, false);
+        f.parts_left.store(p);
+        parts += p;
+    }
+    parts += int64_t(job->waves.size());  // one part per wave for its scatter kernels
+    if (parts == 0) {
+        mark_device_done(job);
+        finish_job_now(job);
+        return TSNAP_OK;
+    }
+    job->parts_left.store(parts);
+    for (Wave& w : job->waves) {
+        int64_t c = 0;
+        for (int fi : w.files) c += int64_t((job->files[fi].nbytes + sb - 1) / sb);
+        w.chunks_to_upload.store(c);
+    }
+    for (size_t i = 0; i < job->files.size(); ++i)
+        if (job->files[i].host_only && job->files[i].nbytes) post_host_file(job, int(i), false);
+
+    auto shared = std::make_shared<LoadShared>();
+    shared->launched.assign(job->waves.size(), 0);
+    const size_t nw = job->waves.size();
+    for (size_t wi = 0; wi < nw; ++wi) {
+        Wave* w = &job->waves[wi];
+        if (wi >= 2) {
+            // the region is reused: wait until the scatter of wave wi-2 has been enqueued, then order
+            // this wave's uploads after it on the device
+            std::unique_lock<std::mutex> g(shared->mu);
+            shared->cv.wait(g, [&] { return shared->launched[wi - 2] != 0; });
+            g.unlock();
+            if (job->waves[wi - 2].ev_done)
+                cudaStreamWaitEvent(eng->s_copy, job->waves[wi - 2].ev_done, 0);
+        }
+        const bool last_wave = (wi + 1 == nw);
+        for (int fi : w->files) {
+            FileSpec* f = &job->files[fi];
+            char* base = eng->arena + w->region_off + f->arena_off;
+            for (uint64_t lo = 0; lo < f->nbytes; lo += sb) {
+                const uint64_t n = std::min(sb, f->nbytes - lo);
+                char* slot = eng->ring.acquire();
+                eng->io->post([eng, job, w, wi, f, base, slot, lo, n, shared, last_wave] {
+                    cudaSetDevice(eng->device);
+                    bool ok = !job->failed();
+                    if (ok && f->mem_src) {
+                        memcpy(slot, f->mem_src + lo, n);
+                    } else if (ok && pread_all(f->fd, slot, n, f->offset + lo) != 0) {
+                        job->fail(TSNAP_EIO, "pread " + f->path + ": " + strerror(errno));
+                        ok = false;
+                    }
+                    cudaEvent_t ev = eng->get_event();
+                    if (ok && cudaMemcpyAsync(base + lo, slot, n, cudaMemcpyHostToDevice, eng->s_copy) != cudaSuccess) {
+                        job->fail(TSNAP_ECUDA, "H2D copy failed to enqueue");
+                        ok = false;
+                    }
+                    cudaEventRecord(ev, eng->s_copy);
+                    eng->bytes_h2d += n;
+                    push_pending(eng, ev, [eng, job, f, slot, n, ev](bool evok) {
+                        eng->put_event(ev);
+                        if (!evok) job->fail(TSNAP_ECUDA, "H2D copy failed");
+                        eng->ring.release(slot);
+                        finish_file_part(job, *f, n, false);
+                    });
+                    // the worker that enqueues the last upload of the wave launches its scatter kernels
+                    if (w->chunks_to_upload.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                        int r = TSNAP_OK;
+                        if (!job->failed()) {
+                            cudaEventCreateWithFlags(&w->ev_copied, cudaEventDisableTiming);
+                            cudaEventRecord(w->ev_copied, eng->s_copy);
+                            cudaStreamWaitEvent(eng->s_kernel, w->ev_copied, 0);
+                            r = launch_wave(job, *w);
+                            if (r != TSNAP_OK) job->fail(r, last_err());
+                        }
+                        {
+                            std::lock_guard<std::mutex> g(shared->mu);
+                            shared->launched[wi] = 1;
+                        }
+                        shared->cv.notify_all();
+                        if (r == TSNAP_OK && w->ev_done && !job->failed()) {
+                            push_pending(eng, w->ev_done, [job, w, last_wave](bool evok) {
+                                if (!evok) job->fail(TSNAP_ECUDA, "scatter kernel failed");
+                                collect_wave_timing(job, *w);
+                                if (last_wave) mark_device_done(job);
+                                job->part_done();
+                            });
+                        } else {
+                            if (last_wave) mark_device_done(job);
+                            job->part_done();
+                        }
+                    }
+                });
+            }
+        }
+    }
+    if (nw == 0) mark_device_done(job);
+    return TSNAP_OK;
+}
+
+// ---- stage (whole-buffer pinned sink) ---------------------------------------------------------------------
+static int run_stage_inner(tsnap_job* job) {
+    tsnap_engine* eng = job->eng;
+    FileSpec& f = job->files[0];
+    auto t0 = clk::now();
+    // host members are copied right here; device members go through the pack kernels
+    std::vector<tsnap_copy_desc> dev;
+    std::string err;
+    for (const tsnap_copy_desc& d : f.members) {
+        if (d.src_space == TSNAP_SPACE_HOST) {
+            NormalizedCopy nc;
+            int rc = normalize_copy(d, uint64_t(uintptr_t(job->stage_buf)), false, &nc, &err);
+            if (rc != TSNAP_OK) return set_err(rc, err);
+            for (int k = 0; k < nc.n; ++k) host_copy_range(nc.m[k], 0, nc.m[k].bytes);
+        } else {
+            dev.push_back(d);
+        }
+    }
+    if (dev.empty() || f.nbytes == 0) {
+        mark_device_done(job);
+        finish_job_now(job);
+        return TSNAP_OK;
+    }
+    if (!eng->has_device) return set_err(TSNAP_ECUDA, "device members on a host-only engine");
+    // device members may be interleaved with host members; pack into the arena image of the whole
+    // buffer and copy back only the spans that device members cover (here: the whole buffer when no
+    // host member exists, else per-member spans)
+    const bool mixed = dev.size() != f.members.size();
+    f.members = dev;
+    int rc = build_waves(job);
+    if (rc != TSNAP_OK) return rc;
+    Wave& w = job->waves[0];
+    rc = plan_wave(job, w, true);
+    if (rc != TSNAP_OK) return rc;
+    job->stats.plan_ms = ms_since(t0);
+    job->parts_left.store(1);
+    if (job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
+    rc = launch_wave(job, w);
+    if (rc != TSNAP_OK) return rc;
+    push_pending(eng, w.ev_done, [job](bool ok) {
+        if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
+        mark_device_done(job);
+    });
+    CUDA_TRY(cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0));
+    const char* base = eng->arena + w.region_off + f.arena_off;
+    char* out = static_cast<char*>(job->stage_buf);
+    if (!mixed) {
+        CUDA_TRY(cudaMemcpyAsync(out, base, f.nbytes, cudaMemcpyDeviceToHost, eng->s_copy));
+        eng->bytes_d2h += f.nbytes;
+    } else {
+        for (const tsnap_copy_desc& d : dev) {
+            uint64_t numel = 1;
+            for (int i = 0; i < d.ndim; ++i) numel *= uint64_t(d.sizes[i]);
+            const uint64_t nb = numel * dtype_size(d.dst_dtype);
+            if (nb == 0) continue;
+            CUDA_TRY(cudaMemcpyAsync(out + d.dst_addr, base + d.dst_addr, nb, cudaMemcpyDeviceToHost, eng->s_copy));
+            eng->bytes_d2h += nb;
+        }
+    }
+    cudaEvent_t ev = eng->get_event();
+    CUDA_TRY(cudaEventRecord(ev, eng->s_copy));
+    Wave* wp = &w;
+    push_pending(eng, ev, [eng, job, ev, wp](bool ok) {
+        eng->put_event(ev);
+        if (!ok) job->fail(TSNAP_ECUDA, "D2H copy failed");
+        collect_wave_timing(job, *wp);
+        job->part_done();
+    });
+    return TSNAP_OK;
+}
+
+static void run_job(tsnap_job* job) {
+    tsnap_engine* eng = job->eng;
+    if (eng->has_device) cudaSetDevice(eng->device);
+    int rc;
+    if (job->kind == kSave) rc = run_save_inner(job);
+    else if (job->kind == kLoad) rc = run_load_inner(job);
+    else rc = run_stage_inner(job);
+    if (rc != TSNAP_OK) {
+        // failed before any asynchronous part was accounted for
+        job->fail(rc, last_err());
+        for (FileSpec& f : job->files)
+            if (f.fd >= 0) {
+                close(f.fd);
+                f.fd = -1;
+            }
+        mark_device_done(job);
+        finish_job_now(job);
+    }
+}
+
+static void drain_main(tsnap_engine* eng) {
+    for (;;) {
+        tsnap_job* job = nullptr;
+        {
+            std::unique_lock<std::mutex> g(eng->q_mu);
+            eng->q_cv.wait(g, [eng] { return eng->stopping || !eng->job_q.empty(); });
+            if (eng->job_q.empty()) return;
+            job = eng->job_q.front();
+            eng->job_q.pop_front();
+        }
+        run_job(job);
+    }
+}
+
+// ==========================================================================================================
+// C ABI
+// ==========================================================================================================
+extern "C" {
+
+int tsnap_abi_version(void) { return TSNAP_ABI_VERSION; }
+const char* tsnap_last_error(void) { return last_err(); }
+size_t tsnap_dtype_size(int dtype) { return dtype_size(dtype); }
+
+int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
+    if (!cfg || !out) return set_err(TSNAP_EINVAL, "null argument");
+    tsnap_engine* eng = new tsnap_engine();
+    eng->cfg = *cfg;
+    eng->device = cfg->device;
+    eng->allow_bulk = !(cfg->flags & TSNAP_ENGINE_NO_BULK);
+    if (cfg->device >= 0) {
+        cudaError_t e = cudaSetDevice(cfg->device);
+        cudaDeviceProp prop;
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, cfg->device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&eng->s_kernel, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&eng->s_copy, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = init_kernels();
+        if (e != cudaSuccess) {
+            std::string msg = std::string("CUDA device ") + std::to_string(cfg->device) +
+                              " is not usable: " + cudaGetErrorString(e);
+            delete eng;
+            return set_err(TSNAP_ECUDA, msg);
+        }
+        if (prop.major < 10) {
+            delete eng;
+            return set_err(TSNAP_ECUDA, "tsnap_b200 kernels are built for sm_100a only");
+        }
+        eng->sm_count = prop.multiProcessorCount;
+        eng->has_device = true;
+        eng->completion_thread = std::thread(completion_main, eng);
+    }
+    eng->io = new WorkerPool(cfg->io_threads > 0 ? cfg->io_threads : 16);
+    eng->drain_thread = std::thread(drain_main, eng);
+    *out = eng;
+    return TSNAP_OK;
+}
+
+int tsnap_engine_trim(tsnap_engine* eng) {
+    if (!eng) return set_err(TSNAP_EINVAL, "null engine");
+    std::lock_guard<std::mutex> g(eng->pin_mu);
+    for (auto& kv : eng->pin_cache) {
+        if (eng->has_device) cudaFreeHost(kv.second);
+        else free(kv.second);
+    }
+    eng->pin_cache.clear();
+    return TSNAP_OK;
+}
+
+int tsnap_engine_destroy(tsnap_engine* eng) {
+    if (!eng) return TSNAP_OK;
+    {
+        std::lock_guard<std::mutex> g(eng->q_mu);
+        eng->stopping = true;
+    }
+    eng->q_cv.notify_all();
+    if (eng->drain_thread.joinable()) eng->drain_thread.join();
+    delete eng->io;  // drains queued I/O
+    eng->io = nullptr;
+    {
+        std::lock_guard<std::mutex> g(eng->c_mu);
+        eng->stopping = true;
+    }
+    eng->c_cv.notify_all();
+    if (eng->completion_thread.joinable()) eng->completion_thread.join();
+    tsnap_engine_trim(eng);
+    if (eng->has_device) {
+        cudaSetDevice(eng->device);
+        cudaStreamSynchronize(eng->s_kernel);
+        cudaStreamSynchronize(eng->s_copy);
+        if (eng->arena) cudaFree(eng->arena);
+        for (cudaEvent_t e : eng->ev_free) cudaEventDestroy(e);
+        cudaStreamDestroy(eng->s_kernel);
+        cudaStreamDestroy(eng->s_copy);
+    }
+    eng->ring.destroy();
+    delete eng;
+    return TSNAP_OK;
+}
+
+int tsnap_engine_get_stats(tsnap_engine* eng, tsnap_engine_stats* out) {
+    if (!eng || !out) return set_err(TSNAP_EINVAL, "null argument");
+    uint64_t pinned = eng->has_device ? eng->ring.total_bytes() : 0;
+    {
+        std::lock_guard<std::mutex> g(eng->pin_mu);
+        for (auto& kv : eng->pin_cache) pinned += kv.first;
+    }
+    out->pinned_bytes = pinned;
+    out->hbm_arena_bytes = eng->arena_bytes;
+    out->kernels_launched = eng->kernels_launched.load();
+    out->bytes_d2h = eng->bytes_d2h.load();
+    out->bytes_h2d = eng->bytes_h2d.load();
+    out->bytes_written = eng->bytes_written.load();
+    out->bytes_read = eng->bytes_read.load();
+    out->sm_count = eng->sm_count;
+    out->device = eng->device;
+    return TSNAP_OK;
+}
+
+static int job_create(tsnap_engine* eng, int kind, tsnap_job** out) {
+    if (!eng || !out) return set_err(TSNAP_EINVAL, "null argument");
+    tsnap_job* j = new tsnap_job();
+    j->eng = eng;
+    j->kind = kind;
+    *out = j;
+    return TSNAP_OK;
+}
+int tsnap_save_job_create(tsnap_engine* eng, tsnap_job** out) { return job_create(eng, kSave, out); }
+int tsnap_load_job_create(tsnap_engine* eng, tsnap_job** out) { return job_create(eng, kLoad, out); }
+
+static int add_file(tsnap_job* job, const char* path, uint64_t offset, uint64_t nbytes, int32_t* idx) {
+    if (!job || !path || !idx) return set_err(TSNAP_EINVAL, "null argument");
+    if (job->submitted) return set_err(TSNAP_ESTATE, "job already submitted");
+    job->files.emplace_back();
+    FileSpec& f = job->files.back();
+    f.path = path;
+    f.offset = offset;
+    f.nbytes = nbytes;
+    *idx = int32_t(job->files.size()) - 1;
+    return TSNAP_OK;
+}
+int tsnap_save_job_add_file(tsnap_job* job, const char* path, uint64_t nbytes, int32_t* file_index) {
+    if (job && job->kind != kSave) return set_err(TSNAP_ESTATE, "not a save job");
+    return add_file(job, path, 0, nbytes, file_index);
+}
+int tsnap_load_job_add_file(tsnap_job* job, const char* path, uint64_t offset, uint64_t nbytes, int32_t* file_index) {
+    if (job && job->kind != kLoad) return set_err(TSNAP_ESTATE, "not a load job");
+    return add_file(job, path, offset, nbytes, file_index);
+}
+
+static int add_member(tsnap_job* job, int32_t fi, const tsnap_copy_desc* d, bool save) {
+    if (!job || !d) return set_err(TSNAP_EINVAL, "null argument");
+    if (job->submitted) return set_err(TSNAP_ESTATE, "job already submitted");
+    if (fi < 0 || size_t(fi) >= job->files.size()) return set_err(TSNAP_EINVAL, "bad file index");
+    if (save ? d->dst_space != TSNAP_SPACE_WIRE : d->src_space != TSNAP_SPACE_WIRE)
+        return set_err(TSNAP_EINVAL, save ? "save members must have a WIRE destination"
+                                          : "load members must have a WIRE source");
+    // validate now so that errors surface at the call site, like the reference's prepare_* would
+    NormalizedCopy nc;
+    std::string err;
+    int rc = normalize_copy(*d, 0, false, &nc, &err);
+    if (rc != TSNAP_OK) return set_err(rc, err);
+    FileSpec& f = job->files[size_t(fi)];
+    uint64_t numel = 1;
+    for (int i = 0; i < d->ndim; ++i) numel *= uint64_t(d->sizes[i]);
+    if (save) {
+        const uint64_t end = d->dst_addr + numel * dtype_size(d->dst_dtype);
+        if (end > f.nbytes) return set_err(TSNAP_EINVAL, "member exceeds the file's wire image");
+    } else if (numel) {
+        // furthest byte touched on the wire side
+        uint64_t last = d->src_addr;
+        for (int i = 0; i < d->ndim; ++i)
+            last += uint64_t(d->sizes[i] - 1) * uint64_t(d->src_strides[i]) * dtype_size(d->src_dtype);
+        if (last + dtype_size(d->src_dtype) > f.nbytes) return set_err(TSNAP_EINVAL, "member reads past the byte range");
+    }
+    f.members.push_back(*d);
+    job->stats.n_members++;
+    return TSNAP_OK;
+}
+int tsnap_save_job_add_member(tsnap_job* job, int32_t file_index, const tsnap_copy_desc* desc) {
+    return add_member(job, file_index, desc, true);
+}
+int tsnap_load_job_add_member(tsnap_job* job, int32_t file_index, const tsnap_copy_desc* desc) {
+    return add_member(job, file_index, desc, false);
+}
+
+static int submit(tsnap_job* job, void* stream, bool is_consumer) {
+    if (!job) return set_err(TSNAP_EINVAL, "null job");
+    if (job->submitted) return set_err(TSNAP_ESTATE, "job already submitted");
+    tsnap_engine* eng = job->eng;
+    job->stats.n_files = job->files.size();
+    bool any_device = false;
+    for (FileSpec& f : job->files) {
+        job->stats.payload_bytes += f.nbytes;
+        bool host = true;
+        for (const tsnap_copy_desc& d : f.members) {
+            const int sp = job->kind == kLoad ? d.dst_space : d.src_space;
+            if (sp != TSNAP_SPACE_HOST) host = false;
+        }
+        if (job->kind == kStage) {
+            f.host_only = false;
+            any_device = any_device || !host;
+            continue;
+        }
+        if (!host) {
+            for (const tsnap_copy_desc& d : f.members) {
+                const int sp = job->kind == kLoad ? d.dst_space : d.src_space;
+                if (sp == TSNAP_SPACE_HOST)
+                    return set_err(TSNAP_EUNSUP, "a file mixes HOST and DEVICE members: " + f.path +
+                                                     " (the batcher keeps CPU and GPU slabs apart, T:batcher.py:300-303)");
+            }
+        }
+        f.host_only = host;
+        any_device = any_device || !host;
+    }
+    if (any_device && !eng->has_device) return set_err(TSNAP_ECUDA, "device members on a host-only engine");
+    if (any_device && !is_consumer) {
+        cudaSetDevice(eng->device);
+        CUDA_TRY(cudaEventCreateWithFlags(&job->ev_producer, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(job->ev_producer, static_cast<cudaStream_t>(stream)));
+    }
+    if (is_consumer) job->consumer_stream = stream;
+    job->submitted = true;
+    job->t_submit = clk::now();
+    {
+        std::lock_guard<std::mutex> g(eng->q_mu);
+        eng->job_q.push_back(job);
+    }
+    eng->q_cv.notify_one();
+    return TSNAP_OK;
+}
+int tsnap_save_job_submit(tsnap_job* job, void* producer_stream) {
+    if (job && job->kind != kSave) return set_err(TSNAP_ESTATE, "not a save job");
+    return submit(job, producer_stream, false);
+}
+int tsnap_load_job_submit(tsnap_job* job, void* consumer_stream) {
+    if (job && job->kind != kLoad) return set_err(TSNAP_ESTATE, "not a load job");
+    return submit(job, consumer_stream, true);
+}
+
+int tsnap_job_wait_device(tsnap_job* job) {
+    if (!job) return set_err(TSNAP_EINVAL, "null job");
+    if (!job->submitted) return set_err(TSNAP_ESTATE, "job not submitted");
+    std::unique_lock<std::mutex> g(job->mu);
+    job->cv.wait(g, [job] { return job->device_done || job->done; });
+    if (job->err_code) return set_err(job->err_code, job->err_msg);
+    return TSNAP_OK;
+}
+int tsnap_job_wait(tsnap_job* job) {
+    if (!job) return set_err(TSNAP_EINVAL, "null job");
+    if (!job->submitted) return set_err(TSNAP_ESTATE, "job not submitted");
+    std::unique_lock<std::mutex> g(job->mu);
+    job->cv.wait(g, [job] { return job->done; });
+    if (job->err_code) return set_err(job->err_code, job->err_msg);
+    return TSNAP_OK;
+}
+int tsnap_job_done(tsnap_job* job) {
+    if (!job) return 1;
+    std::lock_guard<std::mutex> g(job->mu);
+    return job->done ? 1 : 0;
+}
+int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out) {
+    if (!job || !out) return set_err(TSNAP_EINVAL, "null argument");
+    bool collect = false;
+    {
+        std::lock_guard<std::mutex> g(job->mu);
+        if (job->kind == kSave && job->done && !job->timing_collected) {
+            job->timing_collected = true;
+            collect = true;
+        }
+    }
+    if (collect) {
+        if (job->eng->has_device) cudaSetDevice(job->eng->device);
+        for (Wave& w : job->waves) collect_wave_timing(job, w);
+    }
+    std::lock_guard<std::mutex> g(job->mu);
+    *out = job->stats;
+    return TSNAP_OK;
+}
+int tsnap_job_destroy(tsnap_job* job) {
+    if (!job) return TSNAP_OK;
+    if (job->submitted) {
+        std::unique_lock<std::mutex> g(job->mu);
+        job->cv.wait(g, [job] { return job->done; });
+    }
+    if (job->eng->has_device) cudaSetDevice(job->eng->device);
+    for (Wave& w : job->waves) {
+        if (w.ev_k0) cudaEventDestroy(w.ev_k0);
+        if (w.ev_k1) cudaEventDestroy(w.ev_k1);
+        if (w.ev_k2) cudaEventDestroy(w.ev_k2);
+        if (w.ev_done) cudaEventDestroy(w.ev_done);
+        if (w.ev_copied) cudaEventDestroy(w.ev_copied);
+    }
+    if (job->ev_producer) cudaEventDestroy(job->ev_producer);
+    for (FileSpec& f : job->files)
+        if (f.fd >= 0) close(f.fd);
+    delete job;
+    return TSNAP_OK;
+}
+
+// ---- stager / consumer seam ---------------------------------------------------------------------------------
+static void* pin_get(tsnap_engine* eng, size_t nbytes, size_t* cap) {
+    {
+        std::lock_guard<std::mutex> g(eng->pin_mu);
+        size_t best = SIZE_MAX;
+        for (size_t i = 0; i < eng->pin_cache.size(); ++i)
+            if (eng->pin_cache[i].first >= nbytes && (best == SIZE_MAX || eng->pin_cache[i].first < eng->pin_cache[best].first))
+                best = i;
+        if (best != SIZE_MAX && eng->pin_cache[best].first <= 2 * std::max<size_t>(nbytes, 4096)) {
+            auto kv = eng->pin_cache[best];
+            eng->pin_cache.erase(eng->pin_cache.begin() + best);
+            *cap = kv.first;
+            return kv.second;
+        }
+    }
+    size_t c = align_up(std::max<size_t>(nbytes, 4096), 4096);
+    void* p = nullptr;
+    if (eng->has_device) {
+        cudaSetDevice(eng->device);
+        if (cudaHostAlloc(&p, c, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    } else if (posix_memalign(&p, 4096, c) != 0) {
+        return nullptr;
+    }
+    *cap = c;
+    return p;
+}
+
+int tsnap_stage_submit(tsnap_engine* eng, const tsnap_copy_desc* members, int32_t n, uint64_t nbytes,
+                       void* producer_stream, tsnap_buffer** out) {
+    if (!eng || !out || (n > 0 && !members)) return set_err(TSNAP_EINVAL, "null argument");
+    tsnap_job* job = nullptr;
+    int rc = job_create(eng, kStage, &job);
+    if (rc != TSNAP_OK) return rc;
+    int32_t fi;
+    add_file(job, "<stage>", 0, nbytes, &fi);
+    for (int32_t i = 0; i < n; ++i) {
+        if (members[i].dst_space != TSNAP_SPACE_WIRE) {
+            delete job;
+            return set_err(TSNAP_EINVAL, "stage members must have a WIRE destination");
+        }
+        rc = add_member(job, fi, &members[i], true);
+        if (rc != TSNAP_OK) {
+            delete job;
+            return rc;
+        }
+    }
+    job->stage_buf = pin_get(eng, nbytes, &job->stage_cap);
+    if (!job->stage_buf) {
+        delete job;
+        return set_err(TSNAP_ENOMEM, "pinned allocation failed");
+    }
+    rc = submit(job, producer_stream, false);
+    if (rc != TSNAP_OK) {
+        std::lock_guard<std::mutex> g(eng->pin_mu);
+        eng->pin_cache.emplace_back(job->stage_cap, job->stage_buf);
+        delete job;
+        return rc;
+    }
+    tsnap_buffer* b = new tsnap_buffer{job};
+    *out = b;
+    return TSNAP_OK;
+}
+int tsnap_buffer_wait_device(tsnap_buffer* buf) {
+    if (!buf) return set_err(TSNAP_EINVAL, "null buffer");
+    return tsnap_job_wait_device(buf->job);
+}
+int tsnap_buffer_wait(tsnap_buffer* buf, void** host_ptr, uint64_t* nbytes) {
+    if (!buf) return set_err(TSNAP_EINVAL, "null buffer");
+    int rc = tsnap_job_wait(buf->job);
+    if (host_ptr) *host_ptr = buf->job->stage_buf;
+    if (nbytes) *nbytes = buf->job->files[0].nbytes;
+    return rc;
+}
+int tsnap_buffer_release(tsnap_buffer* buf) {
+    if (!buf) return TSNAP_OK;
+    tsnap_job* job = buf->job;
+    tsnap_engine* eng = job->eng;
+    {
+        std::unique_lock<std::mutex> g(job->mu);
+        job->cv.wait(g, [job] { return job->done; });
+    }
+    {
+        std::lock_guard<std::mutex> g(eng->pin_mu);
+        eng->pin_cache.emplace_back(job->stage_cap, job->stage_buf);
+        // keep the cache bounded: drop the largest buffers beyond 8 entries
+        while (eng->pin_cache.size() > 8) {
+            size_t big = 0;
+            for (size_t i = 1; i < eng->pin_cache.size(); ++i)
+                if (eng->pin_cache[i].first > eng->pin_cache[big].first) big = i;
+            if (eng->has_device) cudaFreeHost(eng->pin_cache[big].second);
+            else free(eng->pin_cache[big].second);
+            eng->pin_cache.erase(eng->pin_cache.begin() + big);
+        }
+    }
+    tsnap_job_destroy(job);
+    delete buf;
+    return TSNAP_OK;
+}
+
+int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes, const tsnap_copy_desc* members,
+                  int32_t n, void* consumer_stream) {
+    if (!eng || (nbytes && !host_buf) || (n > 0 && !members)) return set_err(TSNAP_EINVAL, "null argument");
+    (void)consumer_stream;
+    std::string err;
+    // host destinations: plain host execution against the caller's buffer
+    std::vector<tsnap_copy_desc> dev;
+    for (int32_t i = 0; i < n; ++i) {
+        if (members[i].src_space != TSNAP_SPACE_WIRE) return set_err(TSNAP_EINVAL, "consume members must have a WIRE source");
+        if (members[i].dst_space == TSNAP_SPACE_HOST) {
+            NormalizedCopy nc;
+            int rc = normalize_copy(members[i], uint64_t(uintptr_t(host_buf)), false, &nc, &err);
+            if (rc != TSNAP_OK) return set_err(rc, err);
+            for (int k = 0; k < nc.n; ++k) host_copy_range(nc.m[k], 0, nc.m[k].bytes);
+        } else {
+            dev.push_back(members[i]);
+        }
+    }
+    if (dev.empty() || nbytes == 0) return TSNAP_OK;
+    if (!eng->has_device) return set_err(TSNAP_ECUDA, "device members on a host-only engine");
+    // device destinations: a load job whose "file" is the caller's memory
+    tsnap_job* job = nullptr;
+    int rc = job_create(eng, kLoad, &job);
+    if (rc != TSNAP_OK) return rc;
+    int32_t fi;
+    add_file(job, "<memory>", 0, nbytes, &fi);
+    for (const tsnap_copy_desc& d : dev) {
+        rc = add_member(job, fi, &d, false);
+        if (rc != TSNAP_OK) {
+            delete job;
+            return rc;
+        }
+    }
+    job->files[0].mem_src = static_cast<const char*>(host_buf);
+    rc = submit(job, nullptr, true);
+    if (rc != TSNAP_OK) {
+        delete job;
+        return rc;
+    }
+    rc = tsnap_job_wait(job);
+    std::string msg = rc != TSNAP_OK ? std::string(last_err()) : std::string();
+    tsnap_job_destroy(job);
+    if (rc != TSNAP_OK) return set_err(rc, msg);
+    return TSNAP_OK;
+}
+
+// ---- planning introspection + host execution -----------------------------------------------------------------
+int tsnap_plan_describe(const tsnap_copy_desc* members, int32_t n, uint64_t wire_base_align, tsnap_plan_info* out) {
+    if (!out || (n > 0 && !members)) return set_err(TSNAP_EINVAL, "null argument");
+    memset(out, 0, sizeof(*out));
+    std::string err;
+    // a synthetic wire base with the requested alignment residue
+    const uint64_t base = (1ull << 40) + (wire_base_align & 255);
+    for (int32_t i = 0; i < n; ++i) {
+        NormalizedCopy nc;
+        int rc = normalize_copy(members[i], base, true, &nc, &err);
+        if (rc != TSNAP_OK) return set_err(rc, err);
+        const bool host = members[i].src_space == TSNAP_SPACE_HOST || members[i].dst_space == TSNAP_SPACE_HOST;
+        for (int k = 0; k < nc.n; ++k) {
+            const Member& m = nc.m[k];
+            const uint64_t nt = tile_count(m);
+            // every tile range must tile [0, bytes) exactly
+            uint64_t expect = 0;
+            for (uint64_t t = 0; t < nt; ++t) {
+                uint64_t lo, hi;
+                tile_range(m, uint32_t(t), &lo, &hi);
+                if (lo != expect || hi <= lo) return set_err(TSNAP_EINVAL, "internal: tile cover broken");
+                expect = hi;
+            }
+            if (expect != m.bytes) return set_err(TSNAP_EINVAL, "internal: tile cover incomplete");
+            if (host) {
+                out->n_members_host++;
+                out->bytes_host += m.bytes;
+            } else if (m.mode == kModeBulk) {
+                out->n_members_bulk++;
+                out->n_tiles_bulk += nt;
+                out->bytes_bulk += m.bytes;
+            } else {
+                out->n_members_lsu++;
+                out->n_tiles_lsu += nt;
+                out->bytes_lsu += m.bytes;
+            }
+        }
+    }
+    return TSNAP_OK;
+}
+
+int tsnap_host_execute(const tsnap_copy_desc* members, int32_t n, void* wire_buf, uint64_t wire_nbytes,
+                       int32_t threads) {
+    if ((n > 0 && !members) || (!wire_buf && wire_nbytes)) return set_err(TSNAP_EINVAL, "null argument");
+    std::string err;
+    struct Work {
+        Member m;
+        uint64_t lo, hi;
+    };
+    std::vector<Work> work;
+    const uint64_t grain = 8ull << 20;
+    for (int32_t i = 0; i < n; ++i) {
+        const tsnap_copy_desc& d = members[i];
+        if (d.src_space == TSNAP_SPACE_DEVICE || d.dst_space == TSNAP_SPACE_DEVICE)
+            return set_err(TSNAP_EINVAL, "tsnap_host_execute only handles HOST <-> WIRE copies");
+        NormalizedCopy nc;
+        int rc = normalize_copy(d, uint64_t(uintptr_t(wire_buf)), false, &nc, &err);
+        if (rc != TSNAP_OK) return set_err(rc, err);
+        for (int k = 0; k < nc.n; ++k) {
+            const Member& m = nc.m[k];
+            const uint64_t wire_off = (d.dst_space == TSNAP_SPACE_WIRE ? m.dst : m.src) - uint64_t(uintptr_t(wire_buf));
+            if (d.dst_space == TSNAP_SPACE_WIRE && wire_off + m.bytes > wire_nbytes)
+                return set_err(TSNAP_EINVAL, "member exceeds the wire buffer");
+            // grains must not split a destination element of a cast
+            const uint64_t g = grain / 16 * 16;
+            for (uint64_t lo = 0; lo < m.bytes; lo += g) work.push_back({m, lo, std::min(m.bytes, lo + g)});
+        }
+    }
+    if (threads <= 1 || work.size() <= 1) {
+        for (const Work& w : work) host_copy_range(w.m, w.lo, w.hi);
+        return TSNAP_OK;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> ts;
+    const int nt = int(std::min<size_t>(size_t(threads), work.size()));
+    for (int t = 0; t < nt; ++t)
+        ts.emplace_back([&] {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= work.size()) return;
+                host_copy_range(work[i].m, work[i].lo, work[i].hi);
+            }
+        });
+    for (auto& t : ts) t.join();
+    return TSNAP_OK;
+}
+
+}  // extern "C"

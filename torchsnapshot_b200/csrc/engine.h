@@ -1,0 +1,171 @@
+// Engine internals: pinned ring, HBM staging arena, worker pool, jobs.  See include/tsnap_b200.h for
+// the contract and DESIGN.md for the pipeline picture.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "plan.h"
+
+namespace tsnap {
+
+int set_err(int code, const std::string& msg);
+const char* last_err();
+
+class WorkerPool {
+   public:
+    explicit WorkerPool(int n);
+    ~WorkerPool();
+    void post(std::function<void()> fn);
+    int size() const { return int(threads_.size()); }
+
+   private:
+    void run();
+    std::vector<std::thread> threads_;
+    std::deque<std::function<void()>> q_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+// fixed-size pinned slots handed out to in-flight chunks
+class SlotRing {
+   public:
+    int init(size_t slot_bytes, int n, bool pinned);
+    void destroy();
+    char* acquire();  // blocks
+    void release(char* p);
+    size_t slot_bytes() const { return slot_bytes_; }
+    size_t total_bytes() const { return slot_bytes_ * all_.size(); }
+
+   private:
+    size_t slot_bytes_ = 0;
+    bool pinned_ = false;
+    std::vector<char*> all_;
+    std::vector<char*> free_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+};
+
+}  // namespace tsnap
+
+struct tsnap_job;
+
+struct tsnap_engine {
+    tsnap_engine_config cfg{};
+    int device = -1;
+    int sm_count = 0;
+    bool has_device = false;
+    bool allow_bulk = true;
+    cudaStream_t s_kernel = nullptr;  // pack / unpack kernels
+    cudaStream_t s_copy = nullptr;    // D2H / H2D payload copies
+    tsnap::SlotRing ring;
+    tsnap::WorkerPool* io = nullptr;
+    // HBM staging arena (grow-only between jobs)
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    // cached whole-buffer pinned allocations for the stager seam, keyed by capacity
+    std::mutex pin_mu;
+    std::vector<std::pair<size_t, void*>> pin_cache;
+    // job scheduling: one drain thread runs jobs FIFO; one completion thread retires chunk events
+    std::thread drain_thread, completion_thread;
+    std::mutex q_mu;
+    std::condition_variable q_cv;
+    std::deque<tsnap_job*> job_q;
+    struct Pending {
+        cudaEvent_t ev;
+        std::function<void(bool ok)> done;
+    };
+    std::mutex c_mu;
+    std::condition_variable c_cv;
+    std::deque<Pending> pending;
+    bool stopping = false;
+    // event pool
+    std::mutex ev_mu;
+    std::vector<cudaEvent_t> ev_free;
+    cudaEvent_t get_event();
+    void put_event(cudaEvent_t e);
+    // stats
+    std::atomic<uint64_t> kernels_launched{0}, bytes_d2h{0}, bytes_h2d{0}, bytes_written{0}, bytes_read{0};
+};
+
+namespace tsnap {
+
+struct FileSpec {
+    std::string path;
+    uint64_t offset = 0;  // load: first byte of the range inside the file
+    uint64_t nbytes = 0;
+    std::vector<tsnap_copy_desc> members;
+    bool host_only = false;  // every member lives in HOST space
+    int fd = -1;
+    std::atomic<int64_t> parts_left{0};
+    uint64_t arena_off = 0;  // offset inside the wave's arena region
+    int wave = -1;
+    const char* mem_src = nullptr;  // load: the "file" is caller memory (consumer seam)
+    FileSpec() = default;
+    FileSpec(const FileSpec& o)
+        : path(o.path), offset(o.offset), nbytes(o.nbytes), members(o.members), host_only(o.host_only), fd(o.fd),
+          arena_off(o.arena_off), wave(o.wave), mem_src(o.mem_src) {
+        parts_left.store(o.parts_left.load());
+    }
+};
+
+struct Wave {
+    std::vector<int> files;
+    uint64_t bytes = 0;       // arena bytes (256B-aligned file regions)
+    uint64_t region_off = 0;  // offset of the region inside the arena
+    std::vector<Member> members;
+    std::vector<Tile> tiles_bulk, tiles_lsu;
+    void* h_tables = nullptr;  // pinned staging of [members | bulk tiles | lsu tiles]
+    void* d_tables = nullptr;
+    size_t table_bytes = 0;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr;  // kernel timing
+    cudaEvent_t ev_done = nullptr;                                    // kernels finished
+    cudaEvent_t ev_copied = nullptr;                                  // all payload copies of the wave finished
+    std::atomic<int64_t> chunks_to_upload{0};                         // load: H2D chunks not yet issued
+};
+
+enum JobKind { kSave = 0, kLoad = 1, kStage = 2 };
+
+}  // namespace tsnap
+
+struct tsnap_job {
+    tsnap_engine* eng = nullptr;
+    int kind = tsnap::kSave;
+    std::vector<tsnap::FileSpec> files;
+    std::deque<tsnap::Wave> waves;
+    cudaEvent_t ev_producer = nullptr;
+    void* consumer_stream = nullptr;
+    bool submitted = false;
+    // completion state
+    std::mutex mu;
+    std::condition_variable cv;
+    bool device_done = false;
+    bool done = false;
+    int err_code = 0;
+    std::string err_msg;
+    std::atomic<int64_t> parts_left{0};
+    // stager seam (kStage): whole-buffer pinned sink
+    void* stage_buf = nullptr;
+    size_t stage_cap = 0;
+    // stats
+    tsnap_job_stats stats{};
+    bool timing_collected = false;
+    std::chrono::steady_clock::time_point t_submit;
+
+    void fail(int code, const std::string& msg);
+    bool failed();
+    void part_done();
+};
+
+struct tsnap_buffer {
+    tsnap_job* job;
+};

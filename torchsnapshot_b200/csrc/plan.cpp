@@ -1,0 +1,257 @@
+#include "plan.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace tsnap {
+
+static const size_t kDtypeSize[TSNAP_DTYPE_COUNT] = {1, 1, 2, 4, 8, 2, 2, 4, 8, 1};
+
+size_t dtype_size(int dt) {
+    if (dt < 0 || dt >= TSNAP_DTYPE_COUNT) return 0;
+    return kDtypeSize[dt];
+}
+
+static bool is_float(int dt) { return dt == TSNAP_F16 || dt == TSNAP_BF16 || dt == TSNAP_F32 || dt == TSNAP_F64; }
+
+bool cast_supported(int s, int d) {
+    if (s == d) return true;
+    return is_float(s) && is_float(d);
+}
+
+static inline uint64_t lowbit(uint64_t x) { return x & (~x + 1); }
+
+struct Dim {
+    int64_t size, ss, ds;  // strides in bytes
+};
+
+int normalize_copy(const tsnap_copy_desc& d, uint64_t wire_base, bool allow_bulk, NormalizedCopy* out,
+                   std::string* err) {
+    out->n = 0;
+    out->src_space = d.src_space;
+    out->dst_space = d.dst_space;
+    auto fail = [&](int code, const std::string& msg) {
+        if (err) *err = msg;
+        return code;
+    };
+    if (d.ndim < 0 || d.ndim > TSNAP_MAX_DIMS) return fail(TSNAP_EINVAL, "ndim out of range");
+    const size_t es = dtype_size(d.src_dtype), ed = dtype_size(d.dst_dtype);
+    if (es == 0 || ed == 0) return fail(TSNAP_EINVAL, "unknown dtype");
+    if (d.src_space < 0 || d.src_space > TSNAP_SPACE_WIRE || d.dst_space < 0 || d.dst_space > TSNAP_SPACE_WIRE)
+        return fail(TSNAP_EINVAL, "unknown address space");
+    if (d.src_space == TSNAP_SPACE_WIRE && d.dst_space == TSNAP_SPACE_WIRE)
+        return fail(TSNAP_EINVAL, "wire-to-wire copies are not a thing");
+    const bool cast = d.src_dtype != d.dst_dtype;
+    if (cast && !cast_supported(d.src_dtype, d.dst_dtype))
+        return fail(TSNAP_EUNSUP, "unsupported dtype conversion");
+
+    // logical shape; C-contiguous element strides for a WIRE destination
+    int64_t cstride[TSNAP_MAX_DIMS];
+    {
+        int64_t acc = 1;
+        for (int i = d.ndim - 1; i >= 0; --i) {
+            if (d.sizes[i] < 0) return fail(TSNAP_EINVAL, "negative size");
+            cstride[i] = acc;
+            acc *= d.sizes[i];
+        }
+    }
+    uint64_t numel = 1;
+    for (int i = 0; i < d.ndim; ++i) numel *= uint64_t(d.sizes[i]);
+    if (numel == 0) return TSNAP_OK;
+
+    Dim dims[TSNAP_MAX_DIMS];
+    int nd = 0;
+    for (int i = 0; i < d.ndim; ++i) {
+        if (d.sizes[i] == 1) continue;
+        Dim x;
+        x.size = d.sizes[i];
+        int64_t ss = d.src_strides[i];
+        int64_t ds = d.dst_space == TSNAP_SPACE_WIRE ? cstride[i] : d.dst_strides[i];
+        if (ss < 0 || ds < 0) return fail(TSNAP_EINVAL, "negative strides are not supported");
+        if (ds == 0) return fail(TSNAP_EINVAL, "destination stride 0 with size > 1 (overlapping writes)");
+        x.ss = ss * int64_t(es);
+        x.ds = ds * int64_t(ed);
+        // merge with the previous (outer) dim when both sides are dense across the boundary
+        if (nd > 0 && dims[nd - 1].ss == x.ss * x.size && dims[nd - 1].ds == x.ds * x.size) {
+            dims[nd - 1].size *= x.size;
+            dims[nd - 1].ss = x.ss;
+            dims[nd - 1].ds = x.ds;
+        } else {
+            dims[nd++] = x;
+        }
+    }
+
+    Member m;
+    std::memset(&m, 0, sizeof(m));
+    m.src = d.src_addr + (d.src_space == TSNAP_SPACE_WIRE ? wire_base : 0);
+    m.dst = d.dst_addr + (d.dst_space == TSNAP_SPACE_WIRE ? wire_base : 0);
+    m.src_dtype = uint32_t(d.src_dtype);
+    m.dst_dtype = uint32_t(d.dst_dtype);
+    m.src_esz = uint32_t(es);
+    m.dst_esz = uint32_t(ed);
+    m.bytes = numel * ed;
+
+    if (cast) {
+        m.mode = kModeCast;
+        m.unit = uint32_t(ed);
+        if (nd > 0 && dims[nd - 1].ss == int64_t(es) && dims[nd - 1].ds == int64_t(ed)) {
+            m.inner = uint64_t(dims[nd - 1].size);
+            --nd;
+        } else {
+            m.inner = 1;
+        }
+        if (m.src % es) return fail(TSNAP_EINVAL, "cast source is not element aligned");
+    } else {
+        if (nd > 0 && dims[nd - 1].ss == int64_t(es) && dims[nd - 1].ds == int64_t(ed)) {
+            m.inner = uint64_t(dims[nd - 1].size) * ed;
+            --nd;
+        } else {
+            m.inner = ed;
+        }
+    }
+    if (nd > kMaxOuter) return fail(TSNAP_EUNSUP, "too many non-mergeable dimensions");
+    m.nouter = uint32_t(nd);
+    for (int i = 0; i < nd; ++i) {
+        m.osize[i] = dims[i].size;
+        m.sstride[i] = dims[i].ss;
+        m.dstride[i] = dims[i].ds;
+    }
+
+    if (cast) {
+        out->m[0] = m;
+        out->n = 1;
+        return TSNAP_OK;
+    }
+    if (nd == 0) {
+        // one dense run on both sides
+        const bool device_copy = d.src_space != TSNAP_SPACE_HOST && d.dst_space != TSNAP_SPACE_HOST;
+        if (allow_bulk && device_copy && (m.src & 15) == 0 && (m.dst & 15) == 0 && m.bytes >= kBulkMin) {
+            const uint64_t body = m.bytes & ~uint64_t(15);
+            Member b = m;
+            b.mode = kModeBulk;
+            b.bytes = body;
+            b.inner = body;
+            b.unit = 16;
+            out->m[out->n++] = b;
+            if (m.bytes != body) {
+                Member t = m;
+                t.mode = kModeContig;
+                t.src += body;
+                t.dst += body;
+                t.bytes = m.bytes - body;
+                t.inner = t.bytes;
+                t.shift = uint32_t(t.dst & 15);
+                t.unit = 1;
+                out->m[out->n++] = t;
+            }
+            return TSNAP_OK;
+        }
+        m.mode = kModeContig;
+        m.shift = uint32_t(m.dst & 15);
+        m.unit = uint32_t(lowbit(16 | ((m.src - m.dst) & 15)));  // widest load granule that is aligned whenever dst is
+        out->m[0] = m;
+        out->n = 1;
+        return TSNAP_OK;
+    }
+    m.mode = kModeStrided;
+    uint64_t bits = 16 | m.inner | m.src | m.dst;
+    for (int i = 0; i < nd; ++i) bits |= uint64_t(m.sstride[i]) | uint64_t(m.dstride[i]);
+    m.unit = uint32_t(lowbit(bits));
+    out->m[0] = m;
+    out->n = 1;
+    return TSNAP_OK;
+}
+
+// ---- host execution -------------------------------------------------------------------------------------
+
+static inline float bf16_to_f32(uint16_t v) {
+    uint32_t u = uint32_t(v) << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+// round-to-nearest-even, NaN -> 0x7FC0: what torch's CPU path produces (c10::BFloat16)
+static inline uint16_t f32_to_bf16(float f) {
+    if (std::isnan(f)) return 0x7FC0;
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    uint32_t bias = ((u >> 16) & 1) + 0x7FFFu;
+    return uint16_t((u + bias) >> 16);
+}
+
+static inline double load_as_double(const void* p, uint32_t dt) {
+    switch (dt) {
+        case TSNAP_F16: { _Float16 h; std::memcpy(&h, p, 2); return double(float(h)); }
+        case TSNAP_BF16: { uint16_t v; std::memcpy(&v, p, 2); return double(bf16_to_f32(v)); }
+        case TSNAP_F32: { float f; std::memcpy(&f, p, 4); return double(f); }
+        default: { double x; std::memcpy(&x, p, 8); return x; }
+    }
+}
+static inline void store_from(void* p, uint32_t dt, const void* sp, uint32_t sdt) {
+    // convert through float when the source is <= 32 bit (exact), through double otherwise
+    if (sdt == TSNAP_F64) {
+        double x;
+        std::memcpy(&x, sp, 8);
+        switch (dt) {
+            case TSNAP_F16: { _Float16 h = (_Float16)x; std::memcpy(p, &h, 2); break; }
+            case TSNAP_BF16: { uint16_t v = f32_to_bf16(float(x)); std::memcpy(p, &v, 2); break; }
+            case TSNAP_F32: { float f = float(x); std::memcpy(p, &f, 4); break; }
+            default: std::memcpy(p, &x, 8);
+        }
+        return;
+    }
+    float f = float(load_as_double(sp, sdt));
+    switch (dt) {
+        case TSNAP_F16: { _Float16 h = (_Float16)f; std::memcpy(p, &h, 2); break; }
+        case TSNAP_BF16: { uint16_t v = f32_to_bf16(f); std::memcpy(p, &v, 2); break; }
+        case TSNAP_F32: std::memcpy(p, &f, 4); break;
+        default: { double x = double(f); std::memcpy(p, &x, 8); }
+    }
+}
+
+static inline void outer_offsets(const Member& m, uint64_t row, int64_t* so, int64_t* dofs) {
+    int64_t s = 0, d = 0;
+    for (int i = int(m.nouter) - 1; i >= 0; --i) {
+        const uint64_t sz = uint64_t(m.osize[i]);
+        const uint64_t idx = row % sz;
+        row /= sz;
+        s += int64_t(idx) * m.sstride[i];
+        d += int64_t(idx) * m.dstride[i];
+    }
+    *so = s;
+    *dofs = d;
+}
+
+void host_copy_range(const Member& m, uint64_t lo, uint64_t hi) {
+    if (hi > m.bytes) hi = m.bytes;
+    if (lo >= hi) return;
+    const char* src = reinterpret_cast<const char*>(uintptr_t(m.src));
+    char* dst = reinterpret_cast<char*>(uintptr_t(m.dst));
+    if (m.mode == kModeBulk || m.mode == kModeContig) {
+        std::memcpy(dst + lo, src + lo, hi - lo);
+        return;
+    }
+    if (m.mode == kModeStrided) {
+        uint64_t pos = lo;
+        while (pos < hi) {
+            const uint64_t row = pos / m.inner, col = pos % m.inner;
+            uint64_t n = m.inner - col;
+            if (n > hi - pos) n = hi - pos;
+            int64_t so, dofs;
+            outer_offsets(m, row, &so, &dofs);
+            std::memcpy(dst + dofs + col, src + so + col, n);
+            pos += n;
+        }
+        return;
+    }
+    // cast: lo/hi are dst bytes, multiples of the dst element size by construction
+    const uint64_t e0 = lo / m.dst_esz, e1 = hi / m.dst_esz;
+    for (uint64_t e = e0; e < e1; ++e) {
+        const uint64_t row = e / m.inner, col = e % m.inner;
+        int64_t so, dofs;
+        outer_offsets(m, row, &so, &dofs);
+        store_from(dst + dofs + col * m.dst_esz, m.dst_dtype, src + so + col * m.src_esz, m.src_dtype);
+    }
+}
+
+}  // namespace tsnap

@@ -1,0 +1,100 @@
+// Planner: turns tsnap_copy_desc (strided view <-> strided view, torch-style element strides) into
+// normalised members and a tile cover.  Shared by the device kernels (kernels.cu) and the host
+// executor (host_exec.cpp), so the CPU test-suite exercises the same decomposition the GPU runs.
+//
+// What is being restated here: the reference makes every source "contiguous" first
+// (T:batcher.py:156 `tensor.contiguous()`, T:serialization.py:196 `tensor.contiguous()`) and then does
+// a flat byte copy into [byte_range) of the slab (T:batcher.py:157-158); on restore it narrows both
+// sides and calls Tensor.copy_ (T:io_preparers/sharded_tensor.py:285-323).  We never materialise the
+// contiguous temporary: the strided gather/scatter IS the copy.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tsnap_b200.h"
+
+namespace tsnap {
+
+constexpr int kMaxOuter = 8;
+constexpr uint32_t kTileBulk = 64 * 1024;  // bytes of one bulk (TMA) tile
+constexpr uint32_t kTileLsu = 32 * 1024;   // logical dst bytes of one LSU tile
+constexpr uint64_t kBulkMin = 1024;        // contiguous runs shorter than this stay on the LSU path
+
+enum Mode : uint32_t {
+    kModeBulk = 0,     // contiguous both sides, src/dst/bytes all multiples of 16 -> cp.async.bulk G->S->G
+    kModeContig = 1,   // contiguous both sides, arbitrary alignment -> 16B stores + (shifted) loads
+    kModeStrided = 2,  // outer dims x inner contiguous run, `unit`-byte granules
+    kModeCast = 3,     // element-wise dtype conversion, strided both sides
+};
+
+// Device-visible member record.  Addresses are absolute for the space they live in.
+struct alignas(16) Member {
+    uint64_t src;
+    uint64_t dst;
+    uint64_t bytes;  // logical dst bytes
+    uint64_t inner;  // kModeStrided: contiguous run in bytes; kModeCast: contiguous run in ELEMENTS
+    uint32_t mode;
+    uint32_t unit;    // kModeStrided: granule bytes (1,2,4,8,16)
+    uint32_t nouter;
+    uint32_t shift;   // kModeContig: dst & 15 (tile boundaries are dst-16B aligned)
+    uint32_t src_dtype;
+    uint32_t dst_dtype;
+    uint32_t src_esz;
+    uint32_t dst_esz;
+    int64_t osize[kMaxOuter];
+    int64_t sstride[kMaxOuter];  // bytes
+    int64_t dstride[kMaxOuter];  // bytes
+};
+
+struct Tile {
+    uint32_t member;  // index into the member table of the same kernel
+    uint32_t index;   // tile ordinal within the member
+};
+
+inline uint32_t tile_bytes_for(uint32_t mode) { return mode == kModeBulk ? kTileBulk : kTileLsu; }
+
+// number of tiles a member needs
+inline uint64_t tile_count(const Member& m) {
+    if (m.bytes == 0) return 0;
+    if (m.mode == kModeBulk) return (m.bytes + kTileBulk - 1) / kTileBulk;
+    if (m.mode == kModeContig) return (m.bytes + m.shift + kTileLsu - 1) / kTileLsu;
+    return (m.bytes + kTileLsu - 1) / kTileLsu;
+}
+
+// logical byte range [lo, hi) of tile `index` of member m  (host+device identical: see kernels.cu)
+inline void tile_range(const Member& m, uint32_t index, uint64_t* lo, uint64_t* hi) {
+    if (m.mode == kModeBulk) {
+        *lo = uint64_t(index) * kTileBulk;
+        *hi = *lo + kTileBulk;
+    } else if (m.mode == kModeContig) {
+        uint64_t a = uint64_t(index) * kTileLsu;
+        *lo = a > m.shift ? a - m.shift : 0;
+        *hi = a + kTileLsu - m.shift;
+    } else {
+        *lo = uint64_t(index) * kTileLsu;
+        *hi = *lo + kTileLsu;
+    }
+    if (*hi > m.bytes) *hi = m.bytes;
+}
+
+struct NormalizedCopy {
+    // 0, 1 or 2 members (bulk body + contiguous tail)
+    Member m[2];
+    int n = 0;
+    int src_space = 0, dst_space = 0;
+};
+
+// Normalises one descriptor.  `src_base`/`dst_base` are added to WIRE-space addresses (the absolute
+// address of the wire buffer on the side that executes the copy).  Returns 0 or TSNAP_E*; on error
+// `err` holds the reason.  allow_bulk=false keeps everything on LSU modes.
+int normalize_copy(const tsnap_copy_desc& d, uint64_t wire_base, bool allow_bulk, NormalizedCopy* out,
+                   std::string* err);
+
+size_t dtype_size(int dt);
+bool cast_supported(int src_dt, int dst_dt);
+
+// Host execution of one member over logical byte range [lo,hi) (memcpy of runs / scalar casts).
+void host_copy_range(const Member& m, uint64_t lo, uint64_t hi);
+
+}  // namespace tsnap
