@@ -1,2 +1,10 @@
-"""torchsnapshot_b200 — B200-native data plane behind TorchSnapshot's take/async_take/restore API."""
+"""torchsnapshot_b200 — a B200-native data plane behind TorchSnapshot's Snapshot.take / async_take /
+restore and StoragePlugin API.  The device->host drain + serialization (save) and its mirror (restore)
+run as hand-written sm_100a kernels plus a native pinned-memory copy/I-O engine (libtsnap_b200.so);
+the on-disk format is the reference's, byte for byte."""
+from ._native import NativeError, get_engine
+from .snapshot import PendingSnapshot, Snapshot
+from .stateful import AppState, RNGState, StateDict, Stateful
+
 __version__ = "0.1.0"
+__all__ = ["Snapshot", "PendingSnapshot", "Stateful", "StateDict", "RNGState", "AppState", "NativeError", "get_engine", "__version__"]

@@ -506,10 +506,11 @@ static void mark_device_done(tsnap_job* job) {
     }
 }
 
-static void finish_job_now(tsnap_job* job) {
-    // used when nothing asynchronous is outstanding
-    job->parts_left.store(1);
-    job->part_done();
+// parts_left = asynchronous parts + 1: the extra token belongs to the drain thread, which drops it when
+// it no longer touches the job (run_job).  Waiters may destroy the job the moment the count hits zero.
+static void account_parts(tsnap_job* job, int64_t async_parts) {
+    job->parts_left.store(async_parts + 1);
+    job->accounted = true;
 }
 
 static int run_save_inner(tsnap_job* job) {
@@ -533,14 +534,10 @@ static int run_save_inner(tsnap_job* job) {
         f.parts_left.store(p);
         parts += p;
     }
-    if (parts == 0) {
-        mark_device_done(job);
-        finish_job_now(job);
-        return TSNAP_OK;
-    }
     for (Wave& w : job->waves) CUDA_TRY(cudaEventCreateWithFlags(&w.ev_copied, cudaEventDisableTiming));
-    job->parts_left.store(parts);
+    account_parts(job, parts);
     if (job->waves.empty()) mark_device_done(job);
+    if (parts == 0) return TSNAP_OK;
 
     const size_t nw = job->waves.size();
     size_t launched = 0;
@@ -663,12 +660,11 @@ static int run_load_inner(tsnap_job* job) {
         parts += p;
     }
     parts += int64_t(job->waves.size());  // one part per wave for its scatter kernels
+    account_parts(job, parts);
     if (parts == 0) {
         mark_device_done(job);
-        finish_job_now(job);
         return TSNAP_OK;
     }
-    job->parts_left.store(parts);
     for (Wave& w : job->waves) {
         int64_t c = 0;
         for (int fi : w.files) c += int64_t((job->files[fi].nbytes + sb - 1) / sb);
@@ -774,8 +770,8 @@ static int run_stage_inner(tsnap_job* job) {
         }
     }
     if (dev.empty() || f.nbytes == 0) {
+        account_parts(job, 0);
         mark_device_done(job);
-        finish_job_now(job);
         return TSNAP_OK;
     }
     if (!eng->has_device) return set_err(TSNAP_ECUDA, "device members on a host-only engine");
@@ -790,14 +786,9 @@ static int run_stage_inner(tsnap_job* job) {
     rc = plan_wave(job, w, true);
     if (rc != TSNAP_OK) return rc;
     job->stats.plan_ms = ms_since(t0);
-    job->parts_left.store(1);
     if (job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
     rc = launch_wave(job, w);
     if (rc != TSNAP_OK) return rc;
-    push_pending(eng, w.ev_done, [job](bool ok) {
-        if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
-        mark_device_done(job);
-    });
     CUDA_TRY(cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0));
     const char* base = eng->arena + w.region_off + f.arena_off;
     char* out = static_cast<char*>(job->stage_buf);
@@ -817,6 +808,11 @@ static int run_stage_inner(tsnap_job* job) {
     cudaEvent_t ev = eng->get_event();
     CUDA_TRY(cudaEventRecord(ev, eng->s_copy));
     Wave* wp = &w;
+    account_parts(job, 1);
+    push_pending(eng, w.ev_done, [job](bool ok) {
+        if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
+        mark_device_done(job);
+    });
     push_pending(eng, ev, [eng, job, ev, wp](bool ok) {
         eng->put_event(ev);
         if (!ok) job->fail(TSNAP_ECUDA, "D2H copy failed");
@@ -834,16 +830,19 @@ static void run_job(tsnap_job* job) {
     else if (job->kind == kLoad) rc = run_load_inner(job);
     else rc = run_stage_inner(job);
     if (rc != TSNAP_OK) {
-        // failed before any asynchronous part was accounted for
         job->fail(rc, last_err());
-        for (FileSpec& f : job->files)
-            if (f.fd >= 0) {
-                close(f.fd);
-                f.fd = -1;
-            }
         mark_device_done(job);
-        finish_job_now(job);
+        if (!job->accounted) {
+            // failed before any asynchronous part was handed out
+            for (FileSpec& f : job->files)
+                if (f.fd >= 0) {
+                    close(f.fd);
+                    f.fd = -1;
+                }
+            account_parts(job, 0);
+        }
     }
+    job->part_done();  // the drain thread's token: `job` may be destroyed by a waiter from here on
 }
 
 static void drain_main(tsnap_engine* eng) {

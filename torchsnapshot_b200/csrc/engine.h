@@ -145,6 +145,7 @@ struct tsnap_job {
     cudaEvent_t ev_producer = nullptr;
     void* consumer_stream = nullptr;
     bool submitted = false;
+    bool accounted = false;  // parts_left (incl. the drain thread's own token) has been set
     // completion state
     std::mutex mu;
     std::condition_variable cv;

@@ -1,0 +1,36 @@
+"""Thin process-group adapter (T:pg_wrapper.py:17-91): object collectives that degrade to no-ops when
+torch.distributed is not initialised.  Control plane only — KB-sized pickles, latency bound."""
+from __future__ import annotations
+
+from typing import Any, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class PGWrapper:
+    def __init__(self, pg: Optional[dist.ProcessGroup] = None) -> None:
+        self.pg = pg if pg is not None else (dist.group.WORLD if dist.is_available() and dist.is_initialized() else None)
+
+    def get_rank(self) -> int:
+        return 0 if self.pg is None else dist.get_rank(group=self.pg)
+
+    def get_world_size(self) -> int:
+        return 1 if self.pg is None else dist.get_world_size(group=self.pg)
+
+    def barrier(self) -> None:
+        if self.pg is not None:
+            if dist.get_backend(self.pg) == "nccl":
+                dist.barrier(group=self.pg, device_ids=[torch.cuda.current_device()])
+            else:
+                dist.barrier(group=self.pg)
+
+    def broadcast_object_list(self, obj_list: List[Any], src: int = 0) -> None:
+        if self.pg is not None:
+            dist.broadcast_object_list(obj_list, src=dist.get_global_rank(self.pg, src), group=self.pg)
+
+    def all_gather_object(self, obj_list: List[Any], obj: Any) -> None:
+        if self.pg is None:
+            obj_list[0] = obj
+        else:
+            dist.all_gather_object(obj_list, obj, group=self.pg)

@@ -1,0 +1,500 @@
+"""``Snapshot.take / async_take / restore / read_object`` — the reference's public surface
+(T:snapshot.py:67-1068) over the B200 data plane.
+
+Only the orchestration lives here: gather keys, flatten state dicts, plan (prepare_write -> partition ->
+batch), hand the plan to the scheduler/engine, commit ``.snapshot_metadata`` last.  On-disk format and
+collective call pattern follow the reference so that snapshots are interchangeable; the data plane
+underneath is the engine (see scheduler.py)."""
+from __future__ import annotations
+
+import asyncio
+import copy
+import fnmatch
+import functools
+import itertools
+import logging
+import os
+import socket
+import sys
+import threading
+import traceback
+from collections import defaultdict
+from datetime import timedelta
+from typing import Any, Callable, Dict, List, Optional, Set, Tuple, TypeVar
+
+import torch
+import torch.distributed as dist
+from torch.distributed._shard.sharded_tensor import ShardedTensor
+from torch.distributed.tensor import DTensor
+from torch.nn.parallel import DistributedDataParallel as DDP
+
+from .batcher import batch_read_requests, batch_write_requests
+from .flatten import flatten, inflate
+from .io_preparer import is_sharded, prepare_read, prepare_write
+from .io_types import ReadIO, ReadReq, StoragePlugin, WriteIO, WriteReq
+from .knobs import is_batching_disabled
+from .manifest import (
+    SNAPSHOT_FORMAT_VERSION,
+    Entry,
+    Manifest,
+    PrimitiveEntry,
+    SnapshotMetadata,
+    is_container_entry,
+)
+from .manifest_ops import get_manifest_for_rank, handle_sharded_tensor_elasticity
+from .partitioner import consolidate_replicated_entries, partition_write_reqs
+from .pg_wrapper import PGWrapper
+from .scheduler import (
+    _MAX_PER_RANK_MEMORY_BUDGET_BYTES,
+    PendingIOWork,
+    get_process_memory_budget_bytes,
+    sync_execute_read_reqs,
+    sync_execute_write_reqs,
+)
+from .stateful import AppState, RNGState, Stateful
+from .storage_plugin import url_to_storage_plugin_in_event_loop
+
+logger = logging.getLogger(__name__)
+
+SNAPSHOT_METADATA_FNAME = ".snapshot_metadata"
+T = TypeVar("T")
+CustomPrepareFunc = Callable[[str, torch.Tensor, bool], torch.Tensor]
+
+
+class Snapshot:
+    """A handle to a snapshot at ``path``; see :meth:`take`, :meth:`async_take`, :meth:`restore`."""
+
+    def __init__(self, path: str, pg: Optional[dist.ProcessGroup] = None, storage_options: Optional[Dict[str, Any]] = None) -> None:
+        self.path = path
+        self.pg = pg
+        self._storage_options = storage_options
+        self._metadata: Optional[SnapshotMetadata] = None
+
+    # ---- save ---------------------------------------------------------------------------------------
+    @classmethod
+    def take(
+        cls,
+        path: str,
+        app_state: AppState,
+        pg: Optional[dist.ProcessGroup] = None,
+        replicated: Optional[List[str]] = None,
+        storage_options: Optional[Dict[str, Any]] = None,
+        _custom_tensor_prepare_func: Optional[CustomPrepareFunc] = None,
+    ) -> "Snapshot":
+        cls._validate_app_state(app_state)
+        loop = asyncio.new_event_loop()
+        pgw = PGWrapper(pg)
+        path, globs = cls._coalesce_path_and_replicated(path, pgw, app_state, replicated or [])
+        storage = url_to_storage_plugin_in_event_loop(path, loop, storage_options)
+        try:
+            pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, False, _custom_tensor_prepare_func)
+            pending.sync_complete(loop)
+            # commit point: metadata goes last, after every rank finished writing (T:snapshot.py:202-209)
+            pgw.barrier()
+            if pgw.get_rank() == 0:
+                cls._write_snapshot_metadata(metadata, storage, loop)
+        finally:
+            storage.sync_close(loop)
+            loop.close()
+        snap = cls(path=path, pg=pg, storage_options=storage_options)
+        snap._metadata = metadata
+        return snap
+
+    @classmethod
+    def async_take(
+        cls,
+        path: str,
+        app_state: AppState,
+        pg: Optional[dist.ProcessGroup] = None,
+        replicated: Optional[List[str]] = None,
+        storage_options: Optional[Dict[str, Any]] = None,
+        _custom_tensor_prepare_func: Optional[CustomPrepareFunc] = None,
+    ) -> "PendingSnapshot":
+        """Returns once every source tensor has been read — with the engine this is after the pack
+        kernels, i.e. HBM-speed, not host-link speed; the drain and the commit continue in a thread."""
+        cls._validate_app_state(app_state)
+        loop = asyncio.new_event_loop()
+        pgw = PGWrapper(pg)
+        path, globs = cls._coalesce_path_and_replicated(path, pgw, app_state, replicated or [])
+        storage = url_to_storage_plugin_in_event_loop(path, loop, storage_options)
+        try:
+            pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, True, _custom_tensor_prepare_func)
+        except BaseException:
+            storage.sync_close(loop)
+            loop.close()
+            raise
+        return PendingSnapshot(path, pending, pgw, metadata, storage, loop, storage_options)
+
+    @classmethod
+    def _take_impl(
+        cls,
+        path: str,
+        app_state: AppState,
+        replicated: Set[str],
+        pgw: PGWrapper,
+        storage: StoragePlugin,
+        loop: asyncio.AbstractEventLoop,
+        is_async_snapshot: bool,
+        _custom_tensor_prepare_func: Optional[CustomPrepareFunc],
+    ) -> Tuple[PendingIOWork, SnapshotMetadata]:
+        app_state = dict(app_state)
+        rng_item = cls._pop_rng_state(app_state)
+        rng_sd = None
+        manifest: Manifest = {}
+        flattened: Dict[str, Any] = {}
+        # capture the RNG state first and put it back after user code ran (T:snapshot.py:538-574)
+        if rng_item is not None:
+            key, stateful = rng_item
+            rng_sd = stateful.state_dict()
+            m, f = flatten(rng_sd, prefix=key)
+            manifest.update(m)
+            flattened.update(f)
+        rank = pgw.get_rank()
+        for key in cls._gather_keys(list(app_state.keys()), pgw):
+            if key in app_state:
+                m, f = flatten(app_state[key].state_dict(), prefix=key)
+                manifest.update(m)
+                flattened.update(f)
+            pgw.barrier()  # state_dict() may itself run collectives; keep ranks in step
+        if rng_item is not None:
+            rng_item[1].load_state_dict(rng_sd)
+
+        replicated_paths = cls._calculate_replicated_entries(flattened, replicated, pgw)
+        entries: Dict[str, Entry] = {}
+        write_reqs: Dict[str, List[WriteReq]] = {}
+        primitives: Dict[str, PrimitiveEntry] = {}
+        for logical_path, obj in flattened.items():
+            func = functools.partial(_custom_tensor_prepare_func, logical_path) if _custom_tensor_prepare_func is not None else None
+            entry, wrs = prepare_write(obj, logical_path, rank, logical_path in replicated_paths, is_async_snapshot, func)
+            if isinstance(entry, PrimitiveEntry):
+                primitives[logical_path] = entry
+            else:
+                entries[logical_path] = entry
+                write_reqs[logical_path] = wrs
+        entries, write_reqs = partition_write_reqs(entries, write_reqs, pgw)
+        flat_reqs = [wr for wrs in write_reqs.values() for wr in wrs]
+        if not is_batching_disabled():
+            _, flat_reqs = batch_write_requests(list(entries.values()), flat_reqs)
+        manifest.update(primitives)
+        manifest.update(entries)
+        manifest = cls._gather_manifest(manifest, pgw)
+        budget = get_process_memory_budget_bytes(pgw)
+        pending = sync_execute_write_reqs(flat_reqs, storage, budget, rank, loop)
+        metadata = SnapshotMetadata(version=SNAPSHOT_FORMAT_VERSION, world_size=pgw.get_world_size(), manifest=manifest)
+        return pending, metadata
+
+    # ---- restore ------------------------------------------------------------------------------------
+    def restore(self, app_state: AppState, strict: bool = True) -> None:
+        self._validate_app_state(app_state)
+        loop = asyncio.new_event_loop()
+        pgw = PGWrapper(self.pg)
+        storage = url_to_storage_plugin_in_event_loop(self.path, loop, self._storage_options)
+        try:
+            app_state = dict(app_state)
+            rng_item = self._pop_rng_state(app_state)
+            for key in self._gather_keys(list(app_state.keys()), pgw):
+                self._load_stateful(key, app_state.get(key), strict, storage, pgw, loop)
+                pgw.barrier()
+            if rng_item is not None:  # last, so nothing run during restore perturbs it
+                self._load_stateful(rng_item[0], rng_item[1], strict, storage, pgw, loop)
+        finally:
+            storage.sync_close(loop)
+            loop.close()
+
+    def _load_stateful(
+        self, key: str, stateful: Optional[Stateful], strict: bool, storage: StoragePlugin, pgw: PGWrapper, loop: asyncio.AbstractEventLoop
+    ) -> None:
+        if stateful is None:
+            return
+        manifest, merged = get_manifest_for_rank(self.metadata, pgw.get_rank())
+        # load straight into the tensors the stateful already owns (no second copy of the state)
+        _, flat = flatten(stateful.state_dict(), prefix=key)
+        targets = {k: v for k, v in flat.items() if isinstance(v, (torch.Tensor, ShardedTensor, DTensor))}
+        handle_sharded_tensor_elasticity(manifest, merged, list(targets.keys()))
+        state_dict = self._get_state_dict_for_manifest(key, manifest, targets, pgw, storage, loop)
+        if isinstance(stateful, torch.nn.Module):
+            stateful.load_state_dict(state_dict, strict=strict)
+        else:
+            stateful.load_state_dict(state_dict)
+
+    @staticmethod
+    def _get_state_dict_for_manifest(
+        key: str,
+        manifest: Manifest,
+        targets: Dict[str, Any],
+        pgw: PGWrapper,
+        storage: StoragePlugin,
+        loop: asyncio.AbstractEventLoop,
+        replicate_from_rank0: bool = False,
+    ) -> Any:
+        from .flatten import _encode
+
+        root = _encode(key)
+        containers: Manifest = {}
+        read_reqs: List[ReadReq] = []
+        futs = {}
+        for logical_path, entry in manifest.items():
+            if logical_path.split("/", 1)[0] != root:
+                continue
+            if is_container_entry(entry):
+                containers[logical_path] = entry
+                continue
+            rrs, fut = prepare_read(entry, targets.pop(logical_path, None))
+            read_reqs += rrs
+            futs[logical_path] = fut
+        if not is_batching_disabled():
+            read_reqs = batch_read_requests(read_reqs)
+        budget = get_process_memory_budget_bytes(pgw)
+        sync_execute_read_reqs(read_reqs, storage, budget, 0 if replicate_from_rank0 else pgw.get_rank(), loop)
+        return inflate(containers, {k: f.obj for k, f in futs.items()}, prefix=key)
+
+    def get_state_dict_for_key(self, key: str, replicate_from_rank0: bool = False) -> Any:
+        loop = asyncio.new_event_loop()
+        pgw = PGWrapper(self.pg)
+        rank = 0 if replicate_from_rank0 else pgw.get_rank()
+        manifest, _ = get_manifest_for_rank(self.metadata, rank)
+        storage = url_to_storage_plugin_in_event_loop(self.path, loop, self._storage_options)
+        try:
+            return self._get_state_dict_for_manifest(key, manifest, {}, pgw, storage, loop, replicate_from_rank0)
+        finally:
+            storage.sync_close(loop)
+            loop.close()
+
+    def read_object(self, path: str, obj_out: Optional[T] = None, memory_budget_bytes: Optional[int] = None) -> T:
+        rank_str, logical = path.split("/", 1)
+        manifest, merged = get_manifest_for_rank(self.metadata, int(rank_str))
+        if logical not in merged and logical not in manifest:
+            raise RuntimeError(
+                f'The supplied path "{path}" does not exist in the snapshot\'s manifest. '
+                "Please verify the available paths within the snapshot via `snapshot.get_manifest()`."
+            )
+        entry = merged.get(logical) or manifest[logical]
+        if isinstance(entry, PrimitiveEntry):
+            return entry.get_value()  # type: ignore[return-value]
+        loop = asyncio.new_event_loop()
+        pgw = PGWrapper(self.pg)
+        storage = url_to_storage_plugin_in_event_loop(self.path, loop, self._storage_options)
+        try:
+            read_reqs, fut = prepare_read(entry, obj_out, buffer_size_limit_bytes=memory_budget_bytes)
+            if not is_batching_disabled():
+                read_reqs = batch_read_requests(read_reqs)
+            sync_execute_read_reqs(read_reqs, storage, memory_budget_bytes or _MAX_PER_RANK_MEMORY_BUDGET_BYTES, pgw.get_rank(), loop)
+        finally:
+            storage.sync_close(loop)
+            loop.close()
+        return fut.obj
+
+    # ---- metadata -----------------------------------------------------------------------------------
+    @property
+    def metadata(self) -> SnapshotMetadata:
+        if self._metadata is None:
+            loop = asyncio.new_event_loop()
+            storage = url_to_storage_plugin_in_event_loop(self.path, loop, self._storage_options)
+            try:
+                self._metadata = self._read_snapshot_metadata(storage, loop)
+            finally:
+                storage.sync_close(loop)
+                loop.close()
+        return self._metadata
+
+    def get_manifest(self) -> Dict[str, Entry]:
+        return copy.deepcopy(self.metadata.manifest)
+
+    @staticmethod
+    def _write_snapshot_metadata(metadata: SnapshotMetadata, storage: StoragePlugin, loop: asyncio.AbstractEventLoop) -> None:
+        storage.sync_write(WriteIO(path=SNAPSHOT_METADATA_FNAME, buf=metadata.to_yaml().encode("utf-8")), loop)
+
+    @staticmethod
+    def _read_snapshot_metadata(storage: StoragePlugin, loop: asyncio.AbstractEventLoop) -> SnapshotMetadata:
+        rio = ReadIO(path=SNAPSHOT_METADATA_FNAME)
+        try:
+            storage.sync_read(rio, loop)
+        except Exception as e:
+            raise RuntimeError(
+                f"Failed to read {SNAPSHOT_METADATA_FNAME}. Ensure path to snapshot is correct, "
+                "otherwise snapshot is likely incomplete or corrupted."
+            ) from e
+        return SnapshotMetadata.from_yaml(rio.buf.getvalue().decode("utf-8"))
+
+    # ---- control-plane helpers (object collectives; KB-sized) -----------------------------------------
+    @staticmethod
+    def _validate_app_state(app_state: AppState) -> None:
+        for key, value in app_state.items():
+            if not isinstance(value, Stateful):
+                raise TypeError(f"Expected Stateful in app_state for key {key}, got {type(value)}.")
+
+    @staticmethod
+    def _pop_rng_state(app_state: AppState) -> Optional[Tuple[str, RNGState]]:
+        found = [(k, v) for k, v in app_state.items() if isinstance(v, RNGState)]
+        if len(found) > 1:
+            raise RuntimeError(f"Multiple RNGState objects in app state: {[k for k, _ in found]}")
+        if not found:
+            return None
+        del app_state[found[0][0]]
+        return found[0]
+
+    @staticmethod
+    def _gather_keys(keys: List[str], pgw: PGWrapper) -> List[str]:
+        gathered: List[Any] = [None] * pgw.get_world_size()
+        pgw.all_gather_object(gathered, keys)
+        return sorted(set(itertools.chain.from_iterable(gathered)))
+
+    @classmethod
+    def _coalesce_path_and_replicated(cls, path: str, pgw: PGWrapper, app_state: AppState, replicated: List[str]) -> Tuple[str, Set[str]]:
+        box = [path]
+        pgw.broadcast_object_list(box, src=0)
+        if box[0] != path:
+            logger.warning(f"Rank {pgw.get_rank()} specified a path ({path}) different from rank 0 ({box[0]}). Using path specified by rank 0.")
+        globs = cls._infer_replicated(replicated, app_state)
+        everyone: List[Any] = [None] * pgw.get_world_size()
+        pgw.all_gather_object(everyone, globs)
+        return box[0], set.intersection(*map(set, everyone))
+
+    @staticmethod
+    def _infer_replicated(replicated: List[str], app_state: AppState) -> List[str]:
+        """DDP-wrapped modules are replicated by construction (T:snapshot.py:897-912)."""
+        out = list(replicated)
+        if "**" in out:
+            return out
+        for key, val in app_state.items():
+            if isinstance(val, DDP):
+                ignored = set(getattr(val, "parameters_to_ignore", []) or [])
+                if not ignored:
+                    out.append(os.path.join(key, "**"))
+                    continue
+                for name, _ in itertools.chain(val.named_parameters(), val.named_buffers()):
+                    if name not in ignored:
+                        out.append(os.path.join(key, name))
+        return out
+
+    @staticmethod
+    def _calculate_replicated_entries(flattened: Dict[str, Any], replicated: Set[str], pgw: PGWrapper) -> Set[str]:
+        mine = [p for p, v in flattened.items() if not is_sharded(v) and any(fnmatch.fnmatch(p, g) for g in replicated)]
+        everyone: List[Any] = [None] * pgw.get_world_size()
+        pgw.all_gather_object(everyone, mine)
+        box: List[Any] = [[]]
+        if pgw.get_rank() == 0:
+            # replicated only if present on every rank (T:snapshot.py:656-666)
+            count: Dict[str, int] = defaultdict(int)
+            for paths in everyone:
+                for p in paths:
+                    count[p] += 1
+            box = [[p for p in mine if count[p] == pgw.get_world_size()]]
+        pgw.broadcast_object_list(box, src=0)
+        return set(box[0])
+
+    @staticmethod
+    def _gather_manifest(manifest: Dict[str, Entry], pgw: PGWrapper) -> Dict[str, Entry]:
+        per_rank: List[Any] = [None] * pgw.get_world_size()
+        pgw.all_gather_object(per_rank, manifest)
+        per_rank = consolidate_replicated_entries(per_rank)
+        return {os.path.join(str(r), p): e for r, m in enumerate(per_rank) for p, e in m.items()}
+
+
+# ---- async commit ------------------------------------------------------------------------------------
+_store_lock = threading.Lock()
+_store_cache: Dict[int, Any] = {}
+_take_seq = itertools.count()
+
+
+def _commit_store(pgw: PGWrapper):
+    """A key-value store reachable by all ranks of `pgw`, usable from a background thread (collectives are
+    not).  Rank 0 hosts a TCPStore; its address travels by broadcast once per process group."""
+    if pgw.get_world_size() == 1:
+        return None
+    key = id(pgw.pg)
+    with _store_lock:
+        if key in _store_cache:
+            return _store_cache[key]
+    box: List[Any] = [None]
+    if pgw.get_rank() == 0:
+        sock = socket.socket()
+        sock.bind(("", 0))
+        port = sock.getsockname()[1]
+        sock.close()
+        host = os.environ.get("MASTER_ADDR") or socket.gethostname()
+        box = [(host, port)]
+    pgw.broadcast_object_list(box, src=0)
+    host, port = box[0]
+    store = dist.TCPStore(host, port, pgw.get_world_size(), pgw.get_rank() == 0, timedelta(seconds=1800), wait_for_workers=False)
+    with _store_lock:
+        _store_cache[key] = store
+    return store
+
+
+class PendingSnapshot:
+    """Handle returned by :meth:`Snapshot.async_take`; ``wait()`` joins the background drain + commit."""
+
+    DEFAULT_BARRIER_TIMEOUT = timedelta(seconds=1800)
+
+    def __init__(
+        self,
+        path: str,
+        pending_io_work: PendingIOWork,
+        pgw: PGWrapper,
+        metadata: SnapshotMetadata,
+        storage: StoragePlugin,
+        loop: asyncio.AbstractEventLoop,
+        storage_options: Optional[Dict[str, Any]] = None,
+    ) -> None:
+        self.path = path
+        self.pg = pgw.pg
+        self._storage_options = storage_options
+        self._metadata = metadata
+        self.exc_info: Optional[Any] = None
+        self._done = False
+        store = _commit_store(pgw)  # collective: must happen on the caller thread
+        tag = f"tsnap_b200/{path}#{next(_take_seq)}"
+        self.thread = threading.Thread(
+            target=self._complete, args=(pending_io_work, pgw.get_rank(), pgw.get_world_size(), metadata, storage, loop, store, tag), daemon=True
+        )
+        self.thread.start()
+
+    def _complete(self, pending: PendingIOWork, rank: int, world: int, metadata: SnapshotMetadata, storage: StoragePlugin, loop, store, tag: str) -> None:
+        # no collectives here: this is not the thread the process group belongs to
+        err: Optional[str] = None
+        try:
+            try:
+                pending.sync_complete(loop)
+            except Exception as e:
+                err = f"rank {rank}: {e}"
+                self.exc_info = sys.exc_info()
+            if store is None:
+                if err is None:
+                    Snapshot._write_snapshot_metadata(metadata, storage, loop)
+            else:
+                # two-phase: everyone reports; rank 0 commits only if all succeeded; everyone learns the verdict
+                store.set(f"{tag}/arrive/{rank}", "ok" if err is None else f"err:{err}")
+                if rank == 0:
+                    keys = [f"{tag}/arrive/{r}" for r in range(world)]
+                    store.wait(keys, self.DEFAULT_BARRIER_TIMEOUT)
+                    bad = [v for v in (store.get(k).decode() for k in keys) if v != "ok"]
+                    if not bad:
+                        Snapshot._write_snapshot_metadata(metadata, storage, loop)
+                    store.set(f"{tag}/depart", "ok" if not bad else bad[0])
+                store.wait([f"{tag}/depart"], self.DEFAULT_BARRIER_TIMEOUT)
+                verdict = store.get(f"{tag}/depart").decode()
+                if verdict != "ok" and err is None:
+                    raise RuntimeError(f"snapshot aborted by a peer: {verdict}")
+        except Exception:
+            if self.exc_info is None:
+                self.exc_info = sys.exc_info()
+        finally:
+            try:
+                storage.sync_close(loop)
+                loop.close()
+            except Exception:
+                pass
+            self._done = True
+
+    def wait(self) -> Snapshot:
+        self.thread.join()
+        if self.exc_info is not None:
+            formatted = "".join(traceback.format_exception(*self.exc_info))
+            raise RuntimeError(f"Encountered exception while taking snapshot asynchronously:\n{formatted}")
+        snap = Snapshot(path=self.path, pg=self.pg, storage_options=self._storage_options)
+        snap._metadata = self._metadata
+        return snap
+
+    def done(self) -> bool:
+        return self._done
