@@ -166,6 +166,8 @@ typedef struct tsnap_job_stats {
     double device_done_ms;      /* submit -> all device reads complete (blocking window)     */
     double total_ms;            /* submit -> job complete                                    */
     uint64_t table_h2d_bytes;   /* descriptor/tile tables copied host->device                */
+    double copy_ms;             /* CUDA-event span of the payload D2H copies on the copy stream
+                                   (first copy start -> last copy end); 0 for load jobs      */
 } tsnap_job_stats;
 int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
 
@@ -189,6 +191,8 @@ int tsnap_stage_submit(tsnap_engine* eng, const tsnap_copy_desc* members, int32_
 int tsnap_buffer_wait_device(tsnap_buffer* buf);
 int tsnap_buffer_wait(tsnap_buffer* buf, void** host_ptr, uint64_t* nbytes);
 int tsnap_buffer_release(tsnap_buffer* buf);
+/* timing/stat record of the staging job behind `buf` (valid after tsnap_buffer_wait) */
+int tsnap_buffer_get_stats(tsnap_buffer* buf, tsnap_job_stats* out);
 /* consume: scatter a host byte buffer (what StoragePlugin.read produced) into destination views
  * (BufferConsumer.consume_buffer, T:io_types.py:40-49).  Synchronous. */
 int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes,

@@ -103,6 +103,7 @@ class JobStats(C.Structure):
         ("device_done_ms", C.c_double),
         ("total_ms", C.c_double),
         ("table_h2d_bytes", C.c_uint64),
+        ("copy_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -148,6 +149,7 @@ EXPORTED_SYMBOLS = [
     "tsnap_buffer_wait_device",
     "tsnap_buffer_wait",
     "tsnap_buffer_release",
+    "tsnap_buffer_get_stats",
     "tsnap_consume",
     "tsnap_plan_describe",
     "tsnap_host_execute",
@@ -187,6 +189,7 @@ def _load() -> C.CDLL:
     lib.tsnap_buffer_wait_device.argtypes = [vp]
     lib.tsnap_buffer_wait.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.tsnap_buffer_release.argtypes = [vp]
+    lib.tsnap_buffer_get_stats.argtypes = [vp, C.POINTER(JobStats)]
     lib.tsnap_consume.argtypes = [vp, vp, C.c_uint64, C.POINTER(CopyDesc), C.c_int32, vp]
     lib.tsnap_plan_describe.argtypes = [C.POINTER(CopyDesc), C.c_int32, C.c_uint64, C.POINTER(PlanInfo)]
     lib.tsnap_host_execute.argtypes = [C.POINTER(CopyDesc), C.c_int32, vp, C.c_uint64, C.c_int32]
@@ -360,6 +363,11 @@ class StagedBuffer:
         # the memoryview keeps `arr` alive, `arr._owner` keeps this object (and the pinned block) alive
         arr._owner = self
         return memoryview(arr).cast("B")
+
+    def stats(self) -> dict:
+        st = JobStats()
+        check(lib.tsnap_buffer_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
 
     def release(self) -> None:
         if not self._released:

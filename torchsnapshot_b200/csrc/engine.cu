@@ -535,6 +535,10 @@ static int run_save_inner(tsnap_job* job) {
         parts += p;
     }
     for (Wave& w : job->waves) CUDA_TRY(cudaEventCreateWithFlags(&w.ev_copied, cudaEventDisableTiming));
+    if (!job->waves.empty()) {
+        CUDA_TRY(cudaEventCreate(&job->ev_copy_begin));
+        CUDA_TRY(cudaEventCreate(&job->ev_copy_end));
+    }
     account_parts(job, parts);
     if (job->waves.empty()) mark_device_done(job);
     if (parts == 0) return TSNAP_OK;
@@ -584,6 +588,7 @@ static int run_save_inner(tsnap_job* job) {
     for (size_t wi = 0; wi < nw; ++wi) {
         Wave& w = job->waves[wi];
         bool ok = cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0) == cudaSuccess;
+        if (wi == 0) cudaEventRecord(job->ev_copy_begin, eng->s_copy);
         for (int fi : w.files) {
             FileSpec& f = job->files[fi];
             const char* base = eng->arena + w.region_off + f.arena_off;
@@ -610,6 +615,7 @@ static int run_save_inner(tsnap_job* job) {
                 });
             }
         }
+        if (wi + 1 == nw) cudaEventRecord(job->ev_copy_end, eng->s_copy);
         if (cudaEventRecord(w.ev_copied, eng->s_copy) != cudaSuccess) job->fail(TSNAP_ECUDA, "event record failed");
         if (launched < nw) {
             rc = launch_next();
@@ -790,6 +796,9 @@ static int run_stage_inner(tsnap_job* job) {
     rc = launch_wave(job, w);
     if (rc != TSNAP_OK) return rc;
     CUDA_TRY(cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0));
+    CUDA_TRY(cudaEventCreate(&job->ev_copy_begin));
+    CUDA_TRY(cudaEventCreate(&job->ev_copy_end));
+    CUDA_TRY(cudaEventRecord(job->ev_copy_begin, eng->s_copy));
     const char* base = eng->arena + w.region_off + f.arena_off;
     char* out = static_cast<char*>(job->stage_buf);
     if (!mixed) {
@@ -805,6 +814,7 @@ static int run_stage_inner(tsnap_job* job) {
             eng->bytes_d2h += nb;
         }
     }
+    CUDA_TRY(cudaEventRecord(job->ev_copy_end, eng->s_copy));
     cudaEvent_t ev = eng->get_event();
     CUDA_TRY(cudaEventRecord(ev, eng->s_copy));
     Wave* wp = &w;
@@ -1106,17 +1116,24 @@ int tsnap_job_done(tsnap_job* job) {
 }
 int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out) {
     if (!job || !out) return set_err(TSNAP_EINVAL, "null argument");
-    bool collect = false;
+    bool collect = false, copy_collect = false;
     {
         std::lock_guard<std::mutex> g(job->mu);
-        if (job->kind == kSave && job->done && !job->timing_collected) {
+        if (job->done && !job->timing_collected) {
             job->timing_collected = true;
-            collect = true;
+            collect = job->kind == kSave;
+            copy_collect = true;
         }
     }
-    if (collect) {
-        if (job->eng->has_device) cudaSetDevice(job->eng->device);
+    if (job->eng->has_device && (collect || copy_collect)) cudaSetDevice(job->eng->device);
+    if (collect)
         for (Wave& w : job->waves) collect_wave_timing(job, w);
+    if (copy_collect && job->ev_copy_begin && job->ev_copy_end) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, job->ev_copy_begin, job->ev_copy_end) == cudaSuccess) {
+            std::lock_guard<std::mutex> g(job->mu);
+            job->stats.copy_ms = ms;
+        }
     }
     std::lock_guard<std::mutex> g(job->mu);
     *out = job->stats;
@@ -1137,6 +1154,8 @@ int tsnap_job_destroy(tsnap_job* job) {
         if (w.ev_copied) cudaEventDestroy(w.ev_copied);
     }
     if (job->ev_producer) cudaEventDestroy(job->ev_producer);
+    if (job->ev_copy_begin) cudaEventDestroy(job->ev_copy_begin);
+    if (job->ev_copy_end) cudaEventDestroy(job->ev_copy_end);
     for (FileSpec& f : job->files)
         if (f.fd >= 0) close(f.fd);
     delete job;
@@ -1215,6 +1234,10 @@ int tsnap_buffer_wait(tsnap_buffer* buf, void** host_ptr, uint64_t* nbytes) {
     if (host_ptr) *host_ptr = buf->job->stage_buf;
     if (nbytes) *nbytes = buf->job->files[0].nbytes;
     return rc;
+}
+int tsnap_buffer_get_stats(tsnap_buffer* buf, tsnap_job_stats* out) {
+    if (!buf) return set_err(TSNAP_EINVAL, "null buffer");
+    return tsnap_job_get_stats(buf->job, out);
 }
 int tsnap_buffer_release(tsnap_buffer* buf) {
     if (!buf) return TSNAP_OK;

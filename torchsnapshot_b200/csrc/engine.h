@@ -143,6 +143,7 @@ struct tsnap_job {
     std::vector<tsnap::FileSpec> files;
     std::deque<tsnap::Wave> waves;
     cudaEvent_t ev_producer = nullptr;
+    cudaEvent_t ev_copy_begin = nullptr, ev_copy_end = nullptr;  // timing of the payload D2H span
     void* consumer_stream = nullptr;
     bool submitted = false;
     bool accounted = false;  // parts_left (incl. the drain thread's own token) has been set
