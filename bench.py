@@ -301,6 +301,13 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
     e2e_ms = sum(step_ms) / len(step_ms)
     e2e_gbs = payload_total / 1e9 / (e2e_ms / 1e3)
     keep_tag = f"step{args.steps - 1}"  # kept for the restore measurement
+    if args.only_e2e:
+        cleanup(keep_tag)
+        if rank == 0:
+            print(json.dumps({"only_e2e": True, "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
+                              "io_threads": os.environ.get("TSNAP_B200_IO_THREADS"), "slots": os.environ.get("TSNAP_B200_PINNED_SLOTS"),
+                              "slot_bytes": os.environ.get("TSNAP_B200_PINNED_SLOT_BYTES")}), flush=True)
+        return
 
     # -- restore (same snapshot) --
     restore_ms = []
@@ -466,6 +473,7 @@ def main() -> None:
     ap.add_argument("--link-peak-gbs", type=float, default=57.0)
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--only-e2e", action="store_true", help="tuning aid: run only the timed Snapshot.take steps and print a short line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

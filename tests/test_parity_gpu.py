@@ -136,13 +136,24 @@ def test_cuda_sharded_golden_and_reshard(name, tmp_path, pg):
             assert wire_bytes(full[o[0] : o[0] + s[0], o[1] : o[1] + s[1]]) == wire_bytes(sh.tensor)
 
 
-def test_dtype_converting_restore(tmp_path):
-    # restoring a bf16 snapshot into fp32 parameters converts on load (Tensor.copy_ semantics, T:io_preparers/tensor.py:358-360)
-    w = (torch.randn(257, 129, device=DEV) * 5).to(torch.bfloat16)
+def test_dtype_mismatch_follows_reference_semantics(tmp_path, pg):
+    from torch.distributed._shard.sharded_tensor import Shard, ShardedTensor, ShardMetadata
+
+    w = (torch.randn(257, 128, device=DEV) * 5).to(torch.bfloat16)
     snap = B.Snapshot.take(str(tmp_path / "s"), {"state": B.StateDict(w=w)})
-    tgt = B.StateDict(w=torch.zeros(257, 129, device=DEV))
+    # plain tensors: a dtype mismatch is not an in-place load (T:io_preparers/tensor.py:190-198) — the saved
+    # tensor is materialised as saved and handed to load_state_dict
+    tgt = B.StateDict(w=torch.zeros(257, 128, device=DEV))
     snap.restore({"state": tgt})
-    assert torch.equal(tgt["w"], w.float())
+    assert tgt["w"].dtype == torch.bfloat16 and wire_bytes(tgt["w"]) == wire_bytes(w)
+    # sharded targets: pieces are copied with Tensor.copy_ semantics, i.e. converted (T:io_preparers/sharded_tensor.py:316-323);
+    # here the scatter kernel does the bf16 -> fp32 conversion
+    sw = ShardedTensor._init_from_local_shards([Shard(tensor=w.clone(), metadata=ShardMetadata(shard_offsets=[0, 0], shard_sizes=[257, 128], placement=f"rank:0/{DEV}"))], (257, 128))
+    snap2 = B.Snapshot.take(str(tmp_path / "s2"), {"state": B.StateDict(w=sw)})
+    dst = torch.zeros(257, 128, device=DEV)
+    tw = ShardedTensor._init_from_local_shards([Shard(tensor=dst, metadata=ShardMetadata(shard_offsets=[0, 0], shard_sizes=[257, 128], placement=f"rank:0/{DEV}"))], (257, 128))
+    snap2.restore({"state": B.StateDict(w=tw)})
+    assert torch.equal(dst, w.float())
 
 
 def test_gb_scale_round_trip_checksums(tmp_path):

@@ -589,10 +589,30 @@ static int run_save_inner(tsnap_job* job) {
         Wave& w = job->waves[wi];
         bool ok = cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0) == cudaSuccess;
         if (wi == 0) cudaEventRecord(job->ev_copy_begin, eng->s_copy);
-        for (int fi : w.files) {
-            FileSpec& f = job->files[fi];
+        // Chunks of one file serialise on the inode lock when written concurrently (buffered writes take
+        // i_rwsem exclusively), so consecutive chunks are taken from different files: groups of G files
+        // are drained round-robin, G = number of I/O workers.
+        struct ChunkRef {
+            int fi;
+            uint64_t lo;
+        };
+        std::vector<ChunkRef> order;
+        {
+            const size_t G = size_t(std::max(1, eng->io->size()));
+            for (size_t g0 = 0; g0 < w.files.size(); g0 += G) {
+                const size_t g1 = std::min(w.files.size(), g0 + G);
+                uint64_t maxb = 0;
+                for (size_t i = g0; i < g1; ++i) maxb = std::max(maxb, job->files[w.files[i]].nbytes);
+                for (uint64_t lo = 0; lo < maxb; lo += sb)
+                    for (size_t i = g0; i < g1; ++i)
+                        if (lo < job->files[w.files[i]].nbytes) order.push_back({w.files[i], lo});
+            }
+        }
+        for (const ChunkRef& cr : order) {
+            FileSpec& f = job->files[cr.fi];
             const char* base = eng->arena + w.region_off + f.arena_off;
-            for (uint64_t lo = 0; lo < f.nbytes; lo += sb) {
+            {
+                const uint64_t lo = cr.lo;
                 const uint64_t n = std::min(sb, f.nbytes - lo);
                 char* slot = eng->ring.acquire();
                 cudaEvent_t ev = eng->get_event();
