@@ -3,8 +3,9 @@ restore and StoragePlugin API.  The device->host drain + serialization (save) an
 run as hand-written sm_100a kernels plus a native pinned-memory copy/I-O engine (libtsnap_b200.so);
 the on-disk format is the reference's, byte for byte."""
 from ._native import NativeError, get_engine
+from .integration import install, uninstall
 from .snapshot import PendingSnapshot, Snapshot
 from .stateful import AppState, RNGState, StateDict, Stateful
 
 __version__ = "0.1.0"
-__all__ = ["Snapshot", "PendingSnapshot", "Stateful", "StateDict", "RNGState", "AppState", "NativeError", "get_engine", "__version__"]
+__all__ = ["Snapshot", "PendingSnapshot", "Stateful", "StateDict", "RNGState", "AppState", "NativeError", "get_engine", "install", "uninstall", "__version__"]

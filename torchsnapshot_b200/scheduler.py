@@ -29,6 +29,7 @@ import torch
 from . import _native
 from .io_types import ReadIO, ReadReq, StoragePlugin, WriteIO, WriteReq
 from .knobs import get_max_per_rank_io_concurrency, get_memory_budget_override
+from .native_plan import describe_consumer, describe_stager, native_root as _native_root
 from .pg_wrapper import PGWrapper
 
 logger = logging.getLogger(__name__)
@@ -54,10 +55,6 @@ def get_process_memory_budget_bytes(pg: PGWrapper) -> int:
 
 
 # ---- routing -------------------------------------------------------------------------------------
-def _native_root(storage: StoragePlugin) -> Optional[str]:
-    return getattr(storage, "native_root", None)
-
-
 def _engine_key(tensors: List[torch.Tensor]) -> int:
     for t in tensors:
         if t.is_cuda:
@@ -153,13 +150,12 @@ async def execute_write_reqs(
     generic: List[WriteReq] = []
     total = 0
     for wr in write_reqs:
-        st = wr.buffer_stager
-        if root is not None and hasattr(st, "native_descs") and st.is_raw():
-            descs, keep = st.native_descs(0)
+        described = describe_stager(wr.buffer_stager) if root is not None else None
+        if described is not None:
+            descs, keep, nbytes = described
             if native is None:
                 native = _NativeJobs(save=True)
             job = native.job_for(_engine_key(keep))
-            nbytes = st.wire_nbytes()
             fi = job.add_file(os.path.join(root, wr.path), nbytes)
             for d in descs:
                 job.add_member(fi, d)
@@ -236,13 +232,13 @@ async def execute_read_reqs(read_reqs: List[ReadReq], storage: StoragePlugin, me
     generic: List[ReadReq] = []
     total = 0
     for rr in read_reqs:
-        c = rr.buffer_consumer
-        if root is not None and hasattr(c, "native_descs") and c.is_raw():
-            descs, keep = c.native_descs(0)
+        described = describe_consumer(rr.buffer_consumer) if root is not None else None
+        if described is not None:
+            descs, keep, wire_nbytes = described
             if rr.byte_range is not None:
                 lo, hi = rr.byte_range
             else:
-                lo, hi = 0, c.wire_nbytes() if hasattr(c, "wire_nbytes") else os.path.getsize(os.path.join(root, rr.path))
+                lo, hi = 0, wire_nbytes
             if not descs:
                 continue
             if native is None:
