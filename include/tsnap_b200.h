@@ -166,6 +166,9 @@ typedef struct tsnap_job_stats {
     double device_done_ms;      /* submit -> all device reads complete (blocking window)     */
     double total_ms;            /* submit -> job complete                                    */
     uint64_t table_h2d_bytes;   /* descriptor/tile tables copied host->device                */
+    double slot_wait_ms;        /* time the drain thread was blocked waiting for a free pinned slot   */
+    double io_busy_ms;          /* sum over I/O workers of time inside pwrite/pread                   */
+    double io_queue_ms;         /* sum over chunks of (write start - D2H complete): I/O queueing delay */
     double copy_ms;             /* CUDA-event span of the payload D2H copies on the copy stream
                                    (first copy start -> last copy end); 0 for load jobs      */
 } tsnap_job_stats;

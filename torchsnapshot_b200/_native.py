@@ -103,6 +103,9 @@ class JobStats(C.Structure):
         ("device_done_ms", C.c_double),
         ("total_ms", C.c_double),
         ("table_h2d_bytes", C.c_uint64),
+        ("slot_wait_ms", C.c_double),
+        ("io_busy_ms", C.c_double),
+        ("io_queue_ms", C.c_double),
         ("copy_ms", C.c_double),
     ]
 
@@ -481,10 +484,14 @@ def get_engine(device: int = -1, **kwargs) -> Engine:
         eng = _engines.get(key)
         if eng is None:
             env = os.environ
+            # the kernel's buffered-write path on the measured hosts peaks at ~16 concurrent writers per box
+            # and degrades beyond (profiles/r01_host_write_probe.json), so ranks sharing a host split them
+            local_world = max(1, int(env.get("LOCAL_WORLD_SIZE", "1")))
+            default_io = max(2, 16 // local_world)
             opts = dict(
-                io_threads=int(env.get("TSNAP_B200_IO_THREADS", "0")),
+                io_threads=int(env.get("TSNAP_B200_IO_THREADS", str(default_io))),
                 pinned_slot_bytes=int(env.get("TSNAP_B200_PINNED_SLOT_BYTES", "0")),
-                pinned_slots=int(env.get("TSNAP_B200_PINNED_SLOTS", "0")),
+                pinned_slots=int(env.get("TSNAP_B200_PINNED_SLOTS", "64" if local_world == 1 else "32")),
                 flags=int(env.get("TSNAP_B200_ENGINE_FLAGS", "0")),
                 hbm_staging_bytes=int(env.get("TSNAP_B200_HBM_STAGING_BYTES", "0")),
             )

@@ -614,7 +614,9 @@ static int run_save_inner(tsnap_job* job) {
             {
                 const uint64_t lo = cr.lo;
                 const uint64_t n = std::min(sb, f.nbytes - lo);
+                auto tw = clk::now();
                 char* slot = eng->ring.acquire();
+                job->slot_wait_us += int64_t(ms_since(tw) * 1000.0);
                 cudaEvent_t ev = eng->get_event();
                 ok = ok && !job->failed() &&
                      cudaMemcpyAsync(slot, base + lo, n, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess &&
@@ -626,9 +628,13 @@ static int run_save_inner(tsnap_job* job) {
                 push_pending(eng, ev, [eng, job, fp, slot, lo, n, ev](bool evok) {
                     eng->put_event(ev);
                     if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
-                    eng->io->post([eng, job, fp, slot, lo, n] {
+                    auto tq = clk::now();
+                    eng->io->post([eng, job, fp, slot, lo, n, tq] {
+                        job->io_queue_us += int64_t(ms_since(tq) * 1000.0);
+                        auto tb = clk::now();
                         if (!job->failed() && pwrite_all(fp->fd, slot, n, lo) != 0)
                             job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
+                        job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
                         eng->ring.release(slot);
                         finish_file_part(job, *fp, n, true);
                     });
@@ -1156,6 +1162,9 @@ int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out) {
         }
     }
     std::lock_guard<std::mutex> g(job->mu);
+    job->stats.slot_wait_ms = job->slot_wait_us.load() / 1000.0;
+    job->stats.io_busy_ms = job->io_busy_us.load() / 1000.0;
+    job->stats.io_queue_ms = job->io_queue_us.load() / 1000.0;
     *out = job->stats;
     return TSNAP_OK;
 }

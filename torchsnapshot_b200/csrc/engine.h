@@ -161,6 +161,7 @@ struct tsnap_job {
     // stats
     tsnap_job_stats stats{};
     bool timing_collected = false;
+    std::atomic<int64_t> slot_wait_us{0}, io_busy_us{0}, io_queue_us{0};
     std::chrono::steady_clock::time_point t_submit;
 
     void fail(int code, const std::string& msg);
