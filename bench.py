@@ -239,7 +239,7 @@ def run_reference(args, rank: int, world: int, device: torch.device, base_dir: s
                          "restore_gbs": nbytes / 1e9 / (sum(restore_times) / len(restore_times)) if restore_times else None},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------
@@ -304,9 +304,9 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
     if args.only_e2e:
         cleanup(keep_tag)
         if rank == 0:
-            print(json.dumps({"only_e2e": True, "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
+            emit({"only_e2e": True, "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
                               "io_threads": os.environ.get("TSNAP_B200_IO_THREADS"), "slots": os.environ.get("TSNAP_B200_PINNED_SLOTS"),
-                              "slot_bytes": os.environ.get("TSNAP_B200_PINNED_SLOT_BYTES")}), flush=True)
+                              "slot_bytes": os.environ.get("TSNAP_B200_PINNED_SLOT_BYTES")})
         return
 
     # -- restore (same snapshot) --
@@ -458,10 +458,28 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The single JSON line goes to the process's original stdout; everything else (NCCL banners, warnings
+    printed by libraries) was re-routed to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main() -> None:
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # NCCL prints its version banner on fd 1
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -88,11 +88,14 @@ class Snapshot:
         storage = url_to_storage_plugin_in_event_loop(path, loop, storage_options)
         try:
             pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, False, _custom_tensor_prepare_func)
+            # the engine is draining in its own threads: encode the metadata meanwhile (json with indent=2
+            # runs in the pure-Python encoder, ~40 ms for a 300-entry manifest)
+            encoded = metadata.to_yaml().encode("utf-8") if pgw.get_rank() == 0 else None
             pending.sync_complete(loop)
             # commit point: metadata goes last, after every rank finished writing (T:snapshot.py:202-209)
             pgw.barrier()
             if pgw.get_rank() == 0:
-                cls._write_snapshot_metadata(metadata, storage, loop)
+                cls._write_snapshot_metadata(metadata, storage, loop, encoded)
         finally:
             storage.sync_close(loop)
             loop.close()
@@ -301,8 +304,11 @@ class Snapshot:
         return copy.deepcopy(self.metadata.manifest)
 
     @staticmethod
-    def _write_snapshot_metadata(metadata: SnapshotMetadata, storage: StoragePlugin, loop: asyncio.AbstractEventLoop) -> None:
-        storage.sync_write(WriteIO(path=SNAPSHOT_METADATA_FNAME, buf=metadata.to_yaml().encode("utf-8")), loop)
+    def _write_snapshot_metadata(
+        metadata: SnapshotMetadata, storage: StoragePlugin, loop: asyncio.AbstractEventLoop, encoded: Optional[bytes] = None
+    ) -> None:
+        buf = encoded if encoded is not None else metadata.to_yaml().encode("utf-8")
+        storage.sync_write(WriteIO(path=SNAPSHOT_METADATA_FNAME, buf=buf), loop)
 
     @staticmethod
     def _read_snapshot_metadata(storage: StoragePlugin, loop: asyncio.AbstractEventLoop) -> SnapshotMetadata:
