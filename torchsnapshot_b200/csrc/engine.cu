@@ -17,7 +17,9 @@
 // T:storage_plugins/fs.py:28-51.
 #include "engine.h"
 
+#include <ctype.h>
 #include <errno.h>
+#include <sched.h>
 #include <fcntl.h>
 #include <string.h>
 #include <sys/stat.h>
@@ -48,9 +50,77 @@ const char* last_err() { return g_err.c_str(); }
 using clk = std::chrono::steady_clock;
 static double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
 
+// ---- NUMA placement ---------------------------------------------------------------------------------------
+// The pinned ring is first-touched by the drain thread and read by the I/O workers; keeping those threads on
+// the socket the GPU's PCIe root complex belongs to keeps the DMA target and the page-cache copies local.
+static void bind_current_thread(const std::vector<int>& cpus) {
+    if (cpus.empty()) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus)
+        if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+    sched_setaffinity(0, sizeof(set), &set);
+}
+
+static std::vector<int> parse_cpulist(const std::string& s) {
+    std::vector<int> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        while (i < s.size() && !isdigit(s[i])) ++i;
+        if (i >= s.size()) break;
+        int a = 0;
+        while (i < s.size() && isdigit(s[i])) a = a * 10 + (s[i++] - '0');
+        int b = a;
+        if (i < s.size() && s[i] == '-') {
+            ++i;
+            b = 0;
+            while (i < s.size() && isdigit(s[i])) b = b * 10 + (s[i++] - '0');
+        }
+        for (int c = a; c <= b; ++c) out.push_back(c);
+    }
+    return out;
+}
+
+static std::string read_small_file(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return "";
+    char buf[4096];
+    size_t n = fread(buf, 1, sizeof(buf) - 1, f);
+    fclose(f);
+    buf[n] = 0;
+    return buf;
+}
+
+static std::vector<int> gpu_numa_cpus(int device) {
+    const char* env = getenv("TSNAP_B200_NUMA");
+    if (env && env[0] == '0') return {};
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return {};
+    std::string id(bus);
+    for (char& c : id) c = char(tolower(c));
+    std::string node = read_small_file("/sys/bus/pci/devices/" + id + "/numa_node");
+    if (node.empty()) return {};
+    int n = atoi(node.c_str());
+    if (n < 0) return {};
+    std::vector<int> cpus = parse_cpulist(read_small_file("/sys/devices/system/node/node" + std::to_string(n) + "/cpulist"));
+    // respect the affinity the process was started with (taskset / cgroup cpusets)
+    cpu_set_t cur;
+    if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+        std::vector<int> allowed;
+        for (int c : cpus)
+            if (c < CPU_SETSIZE && CPU_ISSET(c, &cur)) allowed.push_back(c);
+        cpus.swap(allowed);
+    }
+    return cpus;
+}
+
 // ---- WorkerPool ---------------------------------------------------------------------------------------
-WorkerPool::WorkerPool(int n) {
-    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { run(); });
+WorkerPool::WorkerPool(int n, const std::vector<int>& cpus) {
+    for (int i = 0; i < n; ++i)
+        threads_.emplace_back([this, cpus] {
+            bind_current_thread(cpus);
+            run();
+        });
 }
 WorkerPool::~WorkerPool() {
     {
@@ -225,6 +295,7 @@ static void push_pending(tsnap_engine* eng, cudaEvent_t ev, std::function<void(b
 }
 
 static void completion_main(tsnap_engine* eng) {
+    bind_current_thread(eng->numa_cpus);
     cudaSetDevice(eng->device);
     for (;;) {
         tsnap_engine::Pending p;
@@ -882,6 +953,7 @@ static void run_job(tsnap_job* job) {
 }
 
 static void drain_main(tsnap_engine* eng) {
+    bind_current_thread(eng->numa_cpus);
     for (;;) {
         tsnap_job* job = nullptr;
         {
@@ -929,9 +1001,10 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
         }
         eng->sm_count = prop.multiProcessorCount;
         eng->has_device = true;
+        eng->numa_cpus = gpu_numa_cpus(cfg->device);
         eng->completion_thread = std::thread(completion_main, eng);
     }
-    eng->io = new WorkerPool(cfg->io_threads > 0 ? cfg->io_threads : 16);
+    eng->io = new WorkerPool(cfg->io_threads > 0 ? cfg->io_threads : 16, eng->numa_cpus);
     eng->drain_thread = std::thread(drain_main, eng);
     *out = eng;
     return TSNAP_OK;

@@ -22,7 +22,7 @@ const char* last_err();
 
 class WorkerPool {
    public:
-    explicit WorkerPool(int n);
+    WorkerPool(int n, const std::vector<int>& cpus);
     ~WorkerPool();
     void post(std::function<void()> fn);
     int size() const { return int(threads_.size()); }
@@ -65,6 +65,7 @@ struct tsnap_engine {
     int sm_count = 0;
     bool has_device = false;
     bool allow_bulk = true;
+    std::vector<int> numa_cpus;  // CPUs of the NUMA node the GPU hangs off (empty = no binding)
     cudaStream_t s_kernel = nullptr;  // pack / unpack kernels
     cudaStream_t s_copy = nullptr;    // D2H / H2D payload copies
     tsnap::SlotRing ring;

@@ -226,66 +226,81 @@ __global__ void __launch_bounds__(32) tsnap_bulk_copy_kernel(const Member* __res
 constexpr int kLsuThreads = 256;
 constexpr int kLsuUnroll = 4;
 
-template <int U>
-__device__ __forceinline__ uint4 load16_granular(const char* p) {
-    // 16 bytes from p, p aligned to U
-    uint4 v;
-    if (U == 16) {
-        v = ld_stream16(p);
-    } else if (U == 8) {
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
-        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p + 8));
-        v = make_uint4(a.x, a.y, b.x, b.y);
-    } else if (U == 4) {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-        v = make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
-    } else if (U == 2) {
-        const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = (uint32_t)__ldg(q + 2 * i) | ((uint32_t)__ldg(q + 2 * i + 1) << 16);
-        v = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        const uint8_t* q = reinterpret_cast<const uint8_t*>(p);
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            w[i] = (uint32_t)__ldg(q + 4 * i) | ((uint32_t)__ldg(q + 4 * i + 1) << 8) |
-                   ((uint32_t)__ldg(q + 4 * i + 2) << 16) | ((uint32_t)__ldg(q + 4 * i + 3) << 24);
-        v = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    return v;
-}
-
-template <int U>
-__device__ __forceinline__ void contig_body(const char* __restrict__ s, char* __restrict__ d, uint64_t nvec) {
-    // d is 16B aligned, s is U aligned; nvec 16-byte vectors.  Narrow granules issue 16/U loads per
-    // vector, so they get a shallower unroll to stay inside the register budget.
-    constexpr int kUnroll = U >= 8 ? kLsuUnroll : (U == 4 ? 2 : 1);
-    uint64_t i = threadIdx.x;
-    const uint64_t step = (uint64_t)kLsuThreads * kUnroll;
+// 16 B destination vectors, 16 B aligned source: straight streaming copy
+__device__ __forceinline__ void contig_body_aligned(const char* __restrict__ s, char* __restrict__ d, uint64_t nvec) {
+    const uint64_t i = threadIdx.x;
+    const uint64_t step = (uint64_t)kLsuThreads * kLsuUnroll;
     for (uint64_t base = 0; base < nvec; base += step) {
-        uint4 v[kUnroll];
+        uint4 v[kLsuUnroll];
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k) {
+        for (int k = 0; k < kLsuUnroll; ++k) {
             const uint64_t j = base + i + (uint64_t)k * kLsuThreads;
-            if (j < nvec) v[k] = load16_granular<U>(s + j * 16);
+            if (j < nvec) v[k] = ld_stream16(s + j * 16);
         }
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k) {
+        for (int k = 0; k < kLsuUnroll; ++k) {
             const uint64_t j = base + i + (uint64_t)k * kLsuThreads;
             if (j < nvec) st_stream16(d + j * 16, v[k]);
         }
     }
 }
 
-// source and destination disagree on their position inside a 16 B line: cold path, own frame
-__device__ __noinline__ void contig_body_narrow(const char* s, char* d, uint64_t nvec, uint32_t unit) {
-    switch (unit) {
-        case 8: contig_body<8>(s, d, nvec); break;
-        case 4: contig_body<4>(s, d, nvec); break;
-        case 2: contig_body<2>(s, d, nvec); break;
-        default: contig_body<1>(s, d, nvec); break;
+__device__ __forceinline__ uint4 ld_cached16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// bytes [sh, sh+16) of the 32-byte concatenation lo:hi  (sh = 4*W + r, r in 0..3)
+template <int W>
+__device__ __forceinline__ uint4 shift_window(const uint4& lo, const uint4& hi, uint32_t rbits) {
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint4 o;
+    o.x = __funnelshift_r(w[W + 0], w[W + 1], rbits);
+    o.y = __funnelshift_r(w[W + 1], w[W + 2], rbits);
+    o.z = __funnelshift_r(w[W + 2], w[W + 3], rbits);
+    o.w = __funnelshift_r(w[W + 3], w[(W + 4) & 7], rbits);
+    return o;
+}
+
+// Source and destination disagree on their position inside a 16 B line (slab members are unpadded, so
+// one odd-sized tensor shifts everything after it).  All global accesses stay 16 B wide and aligned: each
+// output vector is cut out of two neighbouring aligned source vectors with funnel shifts.  The second
+// load of every pair is the first load of the next thread, so it is served by L1.  The aligned loads may
+// touch up to 15 bytes before/after the run, but never leave the 16 B lines that hold its bytes.
+template <int W>
+__device__ __forceinline__ void contig_body_shift_w(const char* __restrict__ s, char* __restrict__ d, uint64_t nvec,
+                                                    uint32_t sh) {
+    const char* a = s - sh;  // 16 B aligned
+    const uint32_t rbits = (sh & 3) * 8;
+    const uint64_t i = threadIdx.x;
+    constexpr int kUnroll = 2;
+    const uint64_t step = (uint64_t)kLsuThreads * kUnroll;
+    for (uint64_t base = 0; base < nvec; base += step) {
+        uint4 lo[kUnroll], hi[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            const uint64_t j = base + i + (uint64_t)k * kLsuThreads;
+            if (j < nvec) {
+                lo[k] = ld_cached16(a + j * 16);
+                hi[k] = ld_cached16(a + j * 16 + 16);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            const uint64_t j = base + i + (uint64_t)k * kLsuThreads;
+            if (j < nvec) st_stream16(d + j * 16, shift_window<W>(lo[k], hi[k], rbits));
+        }
+    }
+}
+
+__device__ __noinline__ void contig_body_shift(const char* s, char* d, uint64_t nvec) {
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uint64_t>(s) & 15);
+    switch (sh >> 2) {
+        case 0: contig_body_shift_w<0>(s, d, nvec, sh); break;
+        case 1: contig_body_shift_w<1>(s, d, nvec, sh); break;
+        case 2: contig_body_shift_w<2>(s, d, nvec, sh); break;
+        default: contig_body_shift_w<3>(s, d, nvec, sh); break;
     }
 }
 
@@ -309,8 +324,8 @@ __device__ __forceinline__ void tile_contig(const Member& m, uint32_t index) {
     }
     s += head;
     d += head;
-    if (m.unit == 16) contig_body<16>(s, d, nvec);
-    else contig_body_narrow(s, d, nvec, m.unit);
+    if ((reinterpret_cast<uint64_t>(s) & 15) == 0) contig_body_aligned(s, d, nvec);
+    else contig_body_shift(s, d, nvec);
 }
 
 __device__ __forceinline__ void outer_offsets(const Member& m, uint64_t row, int64_t* so, int64_t* dofs) {
@@ -435,7 +450,7 @@ __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
     }
 }
 
-__global__ void __launch_bounds__(kLsuThreads, 4) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
+__global__ void __launch_bounds__(kLsuThreads, 3) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
                                                                    const Tile* __restrict__ tiles, uint32_t ntiles) {
     __shared__ Member sm;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -458,8 +473,8 @@ __global__ void __launch_bounds__(kLsuThreads, 4) tsnap_lsu_copy_kernel(const Me
                 const uint64_t a = (uint64_t)tl.index * kTileLsu;
                 uint64_t hi = a + kTileLsu;
                 if (hi > sm.bytes) hi = sm.bytes;
-                contig_body<16>(reinterpret_cast<const char*>(sm.src) + a, reinterpret_cast<char*>(sm.dst) + a,
-                                (hi - a) >> 4);
+                contig_body_aligned(reinterpret_cast<const char*>(sm.src) + a, reinterpret_cast<char*>(sm.dst) + a,
+                                    (hi - a) >> 4);
             }
         }
     }
@@ -472,7 +487,7 @@ constexpr int kBulkStages = 3;
 constexpr int kBulkStageBytes = 16 * 1024;
 constexpr int kBulkSmem = kBulkStages * kBulkStageBytes + kBulkStages * 8;
 constexpr int kBulkCtasPerSm = 4;
-constexpr int kLsuCtasPerSm = 8;
+constexpr int kLsuCtasPerSm = 6;
 
 cudaError_t init_kernels() {
     return cudaFuncSetAttribute(tsnap_bulk_copy_kernel<kBulkStages, kBulkStageBytes>,
