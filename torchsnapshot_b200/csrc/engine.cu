@@ -92,8 +92,11 @@ static std::string read_small_file(const std::string& path) {
 }
 
 static std::vector<int> gpu_numa_cpus(int device) {
+    // opt-in: on the measured 2-socket hosts confining the 16 writers to the GPU's socket LOWERED end-to-end
+    // throughput (34 vs 39 GB/s, profiles/r01_ncu_summary.md) — the page-cache copy is memory-bound and
+    // benefits from both sockets' channels — so the default leaves placement to the scheduler
     const char* env = getenv("TSNAP_B200_NUMA");
-    if (env && env[0] == '0') return {};
+    if (!env || env[0] != '1') return {};
     char bus[32] = {0};
     if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return {};
     std::string id(bus);

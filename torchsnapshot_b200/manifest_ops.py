@@ -91,7 +91,9 @@ def get_manifest_for_rank(metadata: SnapshotMetadata, rank: int) -> Tuple[Manife
                 local[path] = e
         for path, e in local.items():
             if isinstance(e, (ShardedTensorEntry, DTensorEntry)):
-                local[path] = merged[path]
+                # fully replicated DTensors are not merged (they have a single shard set); the reference
+                # indexes `merged` unconditionally here (T:manifest_ops.py:82-84) and raises KeyError for them
+                local[path] = merged.get(path, e)
         return local, merged
     # a rank that did not exist at save time: rank 0's view minus everything that is not replicated
     local = dict(per_rank[0])
@@ -116,5 +118,7 @@ def handle_sharded_tensor_elasticity(manifest: Manifest, merged_sd_entries: Dict
             parent, _, key = path.rpartition("/")
             manifest[parent].keys.append(key)
     for path in list(manifest):
-        if isinstance(manifest[path], (ShardedTensorEntry, DTensorEntry)) and path not in wanted:
+        e = manifest[path]
+        # fully replicated DTensors are ordinary replicated state, not elastic shards
+        if isinstance(e, (ShardedTensorEntry, DTensorEntry)) and not is_fully_replicated_entry(e) and path not in wanted:
             del manifest[path]
