@@ -304,7 +304,7 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
     if args.only_e2e:
         cleanup(keep_tag)
         if rank == 0:
-            emit({"only_e2e": True, "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
+            emit({"only_e2e": True, "take_phases_ms": S.LAST_STATS.get("take_phases_ms"), "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
                               "io_threads": os.environ.get("TSNAP_B200_IO_THREADS"), "slots": os.environ.get("TSNAP_B200_PINNED_SLOTS"),
                               "slot_bytes": os.environ.get("TSNAP_B200_PINNED_SLOT_BYTES")})
         return
@@ -451,6 +451,7 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
         "link": {"achieved": payload_local / 1e9 / (d2h_ms / 1e3) if d2h_ms else None, "peak": link_peak, "unit": "GB/s",
                  "frac": (payload_local / 1e9 / (d2h_ms / 1e3)) / link_peak if d2h_ms else None,
                  "peak_source": "pinned cudaMemcpyAsync D2H measured on this pool (profiles/r01_box_probe.json)", "d2h_ms": d2h_ms, "pack_ms": pack_ms},
+        "take_phases_ms": {k: round(v, 2) for k, v in (S.LAST_STATS.get("take_phases_ms") or {}).items()},
         "engine_step": {k: last_stats.get(k) for k in ("plan_ms", "kernel_ms", "copy_ms", "device_done_ms", "total_ms", "n_files", "n_members", "n_tiles_bulk", "n_tiles_lsu", "n_kernel_launches")},
         "gpu_launches": int(launches),
         "clocks": clocks,

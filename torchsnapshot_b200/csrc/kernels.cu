@@ -433,13 +433,76 @@ __device__ __forceinline__ void convert_store(char* p, uint32_t ddt, const char*
     else { const double x = (double)f; store_bytes(p, &x, 8, aligned); }
 }
 
+// dense, 16 B aligned, 2-byte <-> 4-byte float conversions: 8 elements per thread, 16 B accesses
+template <bool kNarrow, bool kBf16>
+__device__ __forceinline__ void cast_dense_vec(const char* __restrict__ s, char* __restrict__ d, uint64_t nelem) {
+    const uint64_t ngroups = nelem >> 3;
+    for (uint64_t g = threadIdx.x; g < ngroups; g += kLsuThreads) {
+        if (kNarrow) {  // fp32 -> bf16 / fp16
+            const uint4 a = ld_stream16(s + g * 32);
+            const uint4 b = ld_stream16(s + g * 32 + 16);
+            const float f[8] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+                                __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w)};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (kBf16) {
+                    const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                    o[i] = *reinterpret_cast<const uint32_t*>(&p);
+                } else {
+                    const __half2 p = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                    o[i] = *reinterpret_cast<const uint32_t*>(&p);
+                }
+            }
+            st_stream16(d + g * 16, make_uint4(o[0], o[1], o[2], o[3]));
+        } else {  // bf16 / fp16 -> fp32
+            const uint4 a = ld_stream16(s + g * 16);
+            const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (kBf16) {
+                    const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                    f[2 * i] = p.x;
+                    f[2 * i + 1] = p.y;
+                } else {
+                    const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                    f[2 * i] = p.x;
+                    f[2 * i + 1] = p.y;
+                }
+            }
+            st_stream16(d + g * 32, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+            st_stream16(d + g * 32 + 16, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+        }
+    }
+}
+
 __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
     const uint64_t lo = (uint64_t)index * kTileLsu;
     uint64_t hi = lo + kTileLsu;
     if (hi > m.bytes) hi = m.bytes;
-    const uint64_t e0 = lo / m.dst_esz, e1 = hi / m.dst_esz;
+    uint64_t e0 = lo / m.dst_esz;
+    const uint64_t e1 = hi / m.dst_esz;
     const char* sb = reinterpret_cast<const char*>(m.src);
     char* db = reinterpret_cast<char*>(m.dst);
+    // fast path: one dense run on both sides, 16 B aligned, fp32 <-> {bf16, fp16}
+    if (m.nouter == 0 && ((m.src | m.dst) & 15) == 0) {
+        const bool narrow = m.src_dtype == TSNAP_F32 && (m.dst_dtype == TSNAP_BF16 || m.dst_dtype == TSNAP_F16);
+        const bool widen = m.dst_dtype == TSNAP_F32 && (m.src_dtype == TSNAP_BF16 || m.src_dtype == TSNAP_F16);
+        if (narrow || widen) {
+            const uint64_t n = e1 - e0;
+            const char* s = sb + e0 * m.src_esz;
+            char* d = db + e0 * m.dst_esz;
+            if (narrow) {
+                if (m.dst_dtype == TSNAP_BF16) cast_dense_vec<true, true>(s, d, n);
+                else cast_dense_vec<true, false>(s, d, n);
+            } else {
+                if (m.src_dtype == TSNAP_BF16) cast_dense_vec<false, true>(s, d, n);
+                else cast_dense_vec<false, false>(s, d, n);
+            }
+            e0 += n & ~uint64_t(7);  // the ragged tail (< 8 elements) goes through the scalar loop below
+        }
+    }
     bool aligned = (m.dst % m.dst_esz) == 0;
     for (uint32_t i = 0; i < m.nouter; ++i) aligned = aligned && ((uint64_t)m.dstride[i] % m.dst_esz) == 0;
     for (uint64_t e = e0 + threadIdx.x; e < e1; e += kLsuThreads) {

@@ -140,6 +140,18 @@ class Snapshot:
         is_async_snapshot: bool,
         _custom_tensor_prepare_func: Optional[CustomPrepareFunc],
     ) -> Tuple[PendingIOWork, SnapshotMetadata]:
+        import time as _time
+
+        from .scheduler import LAST_STATS
+
+        phases: Dict[str, float] = {}
+        _t = [_time.perf_counter()]
+
+        def lap(name: str) -> None:
+            now = _time.perf_counter()
+            phases[name] = phases.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
+
         app_state = dict(app_state)
         rng_item = cls._pop_rng_state(app_state)
         rng_sd = None
@@ -153,7 +165,9 @@ class Snapshot:
             manifest.update(m)
             flattened.update(f)
         rank = pgw.get_rank()
-        for key in cls._gather_keys(list(app_state.keys()), pgw):
+        global_keys = cls._gather_keys(list(app_state.keys()), pgw)
+        lap("gather_keys")
+        for key in global_keys:
             if key in app_state:
                 m, f = flatten(app_state[key].state_dict(), prefix=key)
                 manifest.update(m)
@@ -161,8 +175,10 @@ class Snapshot:
             pgw.barrier()  # state_dict() may itself run collectives; keep ranks in step
         if rng_item is not None:
             rng_item[1].load_state_dict(rng_sd)
+        lap("state_dict+flatten+barrier")
 
         replicated_paths = cls._calculate_replicated_entries(flattened, replicated, pgw)
+        lap("replicated_paths")
         entries: Dict[str, Entry] = {}
         write_reqs: Dict[str, List[WriteReq]] = {}
         primitives: Dict[str, PrimitiveEntry] = {}
@@ -174,15 +190,22 @@ class Snapshot:
             else:
                 entries[logical_path] = entry
                 write_reqs[logical_path] = wrs
+        lap("prepare_write")
         entries, write_reqs = partition_write_reqs(entries, write_reqs, pgw)
+        lap("partition")
         flat_reqs = [wr for wrs in write_reqs.values() for wr in wrs]
         if not is_batching_disabled():
             _, flat_reqs = batch_write_requests(list(entries.values()), flat_reqs)
         manifest.update(primitives)
         manifest.update(entries)
+        lap("batch")
         manifest = cls._gather_manifest(manifest, pgw)
+        lap("gather_manifest")
         budget = get_process_memory_budget_bytes(pgw)
+        lap("memory_budget")
         pending = sync_execute_write_reqs(flat_reqs, storage, budget, rank, loop)
+        lap("execute_until_staged")
+        LAST_STATS["take_phases_ms"] = phases
         metadata = SnapshotMetadata(version=SNAPSHOT_FORMAT_VERSION, world_size=pgw.get_world_size(), manifest=manifest)
         return pending, metadata
 
