@@ -304,7 +304,7 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
     if args.only_e2e:
         cleanup(keep_tag)
         if rank == 0:
-            emit({"only_e2e": True, "take_phases_ms": S.LAST_STATS.get("take_phases_ms"), "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
+            emit({"only_e2e": True, "take_phases_ms": S.LAST_STATS.get("take_phases_ms"), "write_phases_ms": S.LAST_STATS.get("write_phases_ms"), "e2e_gbs": e2e_gbs, "e2e_ms": e2e_ms, "steps_ms": step_ms, "engine_step": last_stats,
                               "io_threads": os.environ.get("TSNAP_B200_IO_THREADS"), "slots": os.environ.get("TSNAP_B200_PINNED_SLOTS"),
                               "slot_bytes": os.environ.get("TSNAP_B200_PINNED_SLOT_BYTES")})
         return
@@ -396,6 +396,16 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
 
     if rank != 0:
         return
+    traffic = args.ncu_traffic_bytes
+    if traffic is None:
+        # per-launch DRAM traffic of the same kernel on the same workload from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                cap = json.load(f)
+            if cap.get("payload_bytes_per_rank") == int(payload_local):
+                traffic = cap["traffic_bytes"]
+        except Exception:
+            traffic = None
     peaks, peaks_src = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # dominant kernel = the bulk (TMA) pack kernel; per launch it moves this rank's payload twice (read + write)
@@ -446,12 +456,13 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
             "frac": achieved / hbm_peak if hbm_peak else None,
             "algorithmic_bytes_per_launch": bulk_bytes,
             "launch_ms": bulk_ms,
-            "traffic": args.ncu_traffic_bytes,
+            "traffic": traffic,
         },
         "link": {"achieved": payload_local / 1e9 / (d2h_ms / 1e3) if d2h_ms else None, "peak": link_peak, "unit": "GB/s",
                  "frac": (payload_local / 1e9 / (d2h_ms / 1e3)) / link_peak if d2h_ms else None,
                  "peak_source": "pinned cudaMemcpyAsync D2H measured on this pool (profiles/r01_box_probe.json)", "d2h_ms": d2h_ms, "pack_ms": pack_ms},
         "take_phases_ms": {k: round(v, 2) for k, v in (S.LAST_STATS.get("take_phases_ms") or {}).items()},
+        "write_phases_ms": {k: round(v, 2) for k, v in (S.LAST_STATS.get("write_phases_ms") or {}).items()},
         "engine_step": {k: last_stats.get(k) for k in ("plan_ms", "kernel_ms", "copy_ms", "device_done_ms", "total_ms", "n_files", "n_members", "n_tiles_bulk", "n_tiles_lsu", "n_kernel_launches")},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -144,6 +144,14 @@ async def execute_write_reqs(
     write_reqs: List[WriteReq], storage: StoragePlugin, memory_budget_bytes: int, rank: int
 ) -> PendingIOWork:
     begin = time.monotonic()
+    phases: Dict[str, float] = {}
+    t_mark = [time.perf_counter()]
+
+    def lap(name: str) -> None:
+        now = time.perf_counter()
+        phases[name] = (now - t_mark[0]) * 1e3
+        t_mark[0] = now
+
     loop = asyncio.get_running_loop()
     root = _native_root(storage)
     native: Optional[_NativeJobs] = None
@@ -163,8 +171,10 @@ async def execute_write_reqs(
             total += nbytes
         else:
             generic.append(wr)
+    lap("describe+build_job")
     if native is not None:
         native.submit()
+    lap("submit")
 
     # generic pipeline: budget-gated staging, bounded concurrent writes
     io_tasks: Set[asyncio.Task] = set()
@@ -212,8 +222,11 @@ async def execute_write_reqs(
             await asyncio.gather(*staging)
         executor.shutdown(wait=False)
 
+    lap("generic_staging")
     if native is not None:
         await loop.run_in_executor(None, native.wait_device)
+    lap("wait_device")
+    LAST_STATS["write_phases_ms"] = phases
     logger.info(f"Rank {rank} completed staging in {time.monotonic() - begin:.2f} seconds")
     return PendingIOWork(native, io_tasks, begin, rank, total)
 
