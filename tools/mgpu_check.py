@@ -1,0 +1,69 @@
+"""Multi-GPU functional check (run under torchrun, NCCL): DDP-replicated state (auto-inferred), per-rank state,
+sharded state, sync + async take, restore, and restore at half the world size (reshard-on-load)."""
+import json, os, shutil, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, torch.distributed as dist
+from torch.distributed._shard.sharded_tensor import Shard, ShardedTensor, ShardMetadata
+from torch.nn.parallel import DistributedDataParallel as DDP
+import torchsnapshot_b200 as B
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dev = torch.device("cuda", local); torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+os.environ["TORCHSNAPSHOT_MAX_CHUNK_SIZE_BYTES_OVERRIDE"] = str(1 << 20)
+box = [tempfile.mkdtemp(prefix="mgpu_") if rank == 0 else None]; dist.broadcast_object_list(box, src=0); root = box[0]
+
+torch.manual_seed(0)  # identical on all ranks
+model = torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 512)).to(dev)
+ddp = DDP(model, device_ids=[local])
+opt = torch.optim.Adam(ddp.parameters(), lr=1e-3)
+ddp(torch.randn(8, 1024, device=dev)).sum().backward(); opt.step()
+rows = 64 * world
+full = torch.arange(rows * 96, dtype=torch.float32).reshape(rows, 96)
+mine = full[rank * 64:(rank + 1) * 64].contiguous().to(dev)
+table = ShardedTensor._init_from_local_shards([Shard(tensor=mine, metadata=ShardMetadata(shard_offsets=[rank * 64, 0], shard_sizes=[64, 96], placement=f"rank:{rank}/cuda:{local}"))], (rows, 96))
+extra = B.StateDict(rank_tag=f"r{rank}", noise=torch.full((1000,), float(rank), device=dev), table=table)
+app = {"model": ddp, "optim": opt, "extra": extra}
+for mode in ("sync", "async"):
+    path = os.path.join(root, mode)
+    if mode == "sync": B.Snapshot.take(path, app, replicated=["optim/**"])
+    else: B.Snapshot.async_take(path, app, replicated=["optim/**"]).wait()
+    dist.barrier(device_ids=[local])
+    meta = json.load(open(os.path.join(path, ".snapshot_metadata")))["manifest"]
+    assert "0/model/module.0.weight" in meta and "1/model/module.0.weight" not in meta, "DDP state must be replicated (stored under rank 0 only)"
+    assert meta["0/model/module.0.weight"]["replicated"] is True
+    # every replicated payload location is written exactly once
+    locs = {}
+    for p, e in meta.items():
+        tes = [e] if e["type"] == "Tensor" else [c["tensor"] for c in e.get("chunks", [])] + [s["tensor"] for s in e.get("shards", [])]
+        for te in tes:
+            key = (te["location"], tuple(te["byte_range"] or ()))
+            assert key not in locs, (p, locs.get(key)); locs[key] = p
+            assert os.path.exists(os.path.join(path, te["location"])), te["location"]
+    # restore into a perturbed copy
+    m2 = torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 512)).to(dev)
+    with torch.no_grad():
+        for p in m2.parameters(): p.add_(1.0)
+    d2 = DDP(m2, device_ids=[local]); o2 = torch.optim.Adam(d2.parameters(), lr=1.0)
+    d2(torch.randn(8, 1024, device=dev)).sum().backward(); o2.step()
+    t2 = ShardedTensor._init_from_local_shards([Shard(tensor=torch.zeros(64, 96, device=dev), metadata=ShardMetadata(shard_offsets=[rank * 64, 0], shard_sizes=[64, 96], placement=f"rank:{rank}/cuda:{local}"))], (rows, 96))
+    e2 = B.StateDict(rank_tag="", noise=torch.zeros(1000, device=dev), table=t2)
+    B.Snapshot(path).restore({"model": d2, "optim": o2, "extra": e2})
+    for (k, a), (_, b) in zip(ddp.state_dict().items(), d2.state_dict().items()): assert torch.equal(a, b), k
+    s1, s2 = opt.state_dict()["state"], o2.state_dict()["state"]
+    for k in s1:
+        for kk in s1[k]: assert torch.equal(s1[k][kk], s2[k][kk]), (k, kk)
+    assert e2["rank_tag"] == f"r{rank}" and torch.equal(e2["noise"], extra["noise"]) and torch.equal(t2.local_shards()[0].tensor, mine)
+    dist.barrier(device_ids=[local])
+# reshard-on-load at half the world size: ranks [0, world/2) each load two saved shards
+if world >= 2 and rank < world // 2:
+    sub_rows = rows // (world // 2)
+    dst = torch.zeros(sub_rows, 96, device=dev)
+    snap = B.Snapshot(os.path.join(root, "sync"))
+    got = snap.read_object("0/extra/table", obj_out=dst.new_zeros(rows, 96))
+    assert torch.equal(got.cpu(), full)
+print(f"rank {rank}: multi-GPU check OK", flush=True)
+dist.barrier(device_ids=[local])
+if rank == 0: shutil.rmtree(root, ignore_errors=True)
+dist.destroy_process_group()
