@@ -217,3 +217,40 @@ def test_interchangeable_with_live_reference(name, tmp_path):
                 assert wire_bytes(a[k]) == wire_bytes(got[k]), k
             else:
                 assert a[k] == got[k], k
+
+
+def test_restore_detects_missing_and_truncated_payload(tmp_path):
+    state = {"a": torch.arange(100_000, dtype=torch.float32), "b": torch.ones(10)}
+    with apply_knobs({"no_batching": 1}):
+        B.Snapshot.take(str(tmp_path / "s"), {"state": B.StateDict(**state)})
+        victim = tmp_path / "s" / "0" / "state" / "a"
+        data = victim.read_bytes()
+        victim.write_bytes(data[: len(data) // 2])  # truncated file: a short read must not pass silently
+        with pytest.raises(Exception):
+            B.Snapshot(str(tmp_path / "s")).restore({"state": B.StateDict(a=torch.zeros(100_000), b=torch.zeros(10))})
+        victim.unlink()
+        with pytest.raises(Exception):
+            B.Snapshot(str(tmp_path / "s")).restore({"state": B.StateDict(a=torch.zeros(100_000), b=torch.zeros(10))})
+
+
+def test_concurrent_takes_from_two_threads(tmp_path):
+    import threading
+
+    states = [{f"t{i}": det_tensor((1000 + i, 37), torch.float32, 10 * k + i) for i in range(20)} for k in range(2)]
+    errs = []
+
+    def work(k):
+        try:
+            for rep in range(3):
+                snap = B.Snapshot.take(str(tmp_path / f"s{k}_{rep}"), {"state": B.StateDict(**states[k])})
+                tgt = B.StateDict(**{n: torch.zeros_like(v) for n, v in states[k].items()})
+                snap.restore({"state": tgt})
+                for n, v in states[k].items():
+                    assert wire_bytes(v) == wire_bytes(tgt[n]), n
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs

@@ -315,7 +315,7 @@ static void completion_main(tsnap_engine* eng) {
 }
 
 // ---- planning of one wave ----------------------------------------------------------------------------------
-static int plan_wave(tsnap_job* job, Wave& w, bool wire_is_dst) {
+static int plan_wave(tsnap_job* job, Wave& w) {
     tsnap_engine* eng = job->eng;
     std::string err;
     for (int fi : w.files) {
@@ -325,7 +325,6 @@ static int plan_wave(tsnap_job* job, Wave& w, bool wire_is_dst) {
             NormalizedCopy nc;
             int rc = normalize_copy(d, wire_base, eng->allow_bulk, &nc, &err);
             if (rc != TSNAP_OK) return set_err(rc, "member of " + f.path + ": " + err);
-            (void)wire_is_dst;
             for (int k = 0; k < nc.n; ++k) {
                 const Member& m = nc.m[k];
                 const uint64_t nt = tile_count(m);
@@ -595,7 +594,7 @@ static int run_save_inner(tsnap_job* job) {
     rc = build_waves(job);
     if (rc != TSNAP_OK) return rc;
     for (Wave& w : job->waves) {
-        rc = plan_wave(job, w, true);
+        rc = plan_wave(job, w);
         if (rc != TSNAP_OK) return rc;
     }
     job->stats.plan_ms = ms_since(t0);
@@ -663,25 +662,23 @@ static int run_save_inner(tsnap_job* job) {
         Wave& w = job->waves[wi];
         bool ok = cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0) == cudaSuccess;
         if (wi == 0) cudaEventRecord(job->ev_copy_begin, eng->s_copy);
-        // Chunks of one file serialise on the inode lock when written concurrently (buffered writes take
-        // i_rwsem exclusively), so consecutive chunks are taken from different files: groups of G files
-        // are drained round-robin, G = number of I/O workers.
+        // Buffered writes take the inode lock exclusively, so two chunks of one file never make progress at
+        // the same time.  Treat every file as a sequential job and spread its chunks evenly over the whole
+        // schedule of the wave: chunk k of a file with c chunks is due at (k + 1/2) / c.  Consecutive chunks of
+        // a 512 MiB piece (16 chunks) then sit ~T/16 positions apart instead of back to back, and the
+        // workers always find chunks of distinct files at the head of the queue.
         struct ChunkRef {
             int fi;
             uint64_t lo;
+            double due;
         };
         std::vector<ChunkRef> order;
-        {
-            const size_t G = size_t(std::max(1, eng->io->size()));
-            for (size_t g0 = 0; g0 < w.files.size(); g0 += G) {
-                const size_t g1 = std::min(w.files.size(), g0 + G);
-                uint64_t maxb = 0;
-                for (size_t i = g0; i < g1; ++i) maxb = std::max(maxb, job->files[w.files[i]].nbytes);
-                for (uint64_t lo = 0; lo < maxb; lo += sb)
-                    for (size_t i = g0; i < g1; ++i)
-                        if (lo < job->files[w.files[i]].nbytes) order.push_back({w.files[i], lo});
-            }
+        for (int fi : w.files) {
+            const uint64_t nb = job->files[fi].nbytes;
+            const uint64_t c = (nb + sb - 1) / sb;
+            for (uint64_t k = 0; k < c; ++k) order.push_back({fi, k * sb, (double(k) + 0.5) / double(c)});
         }
+        std::stable_sort(order.begin(), order.end(), [](const ChunkRef& x, const ChunkRef& y) { return x.due < y.due; });
         for (const ChunkRef& cr : order) {
             FileSpec& f = job->files[cr.fi];
             const char* base = eng->arena + w.region_off + f.arena_off;
@@ -692,8 +689,9 @@ static int run_save_inner(tsnap_job* job) {
                 char* slot = eng->ring.acquire();
                 job->slot_wait_us += int64_t(ms_since(tw) * 1000.0);
                 cudaEvent_t ev = eng->get_event();
+                static const bool dbg_skip_d2h = getenv("TSNAP_B200_DEBUG_SKIP_D2H") != nullptr;  // experiments only
                 ok = ok && !job->failed() &&
-                     cudaMemcpyAsync(slot, base + lo, n, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess &&
+                     (dbg_skip_d2h || cudaMemcpyAsync(slot, base + lo, n, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess) &&
                      cudaEventRecord(ev, eng->s_copy) == cudaSuccess;
                 if (!ok) job->fail(TSNAP_ECUDA, std::string("D2H copy: ") + cudaGetErrorString(cudaGetLastError()));
                 eng->bytes_d2h += n;
@@ -706,7 +704,8 @@ static int run_save_inner(tsnap_job* job) {
                     eng->io->post([eng, job, fp, slot, lo, n, tq] {
                         job->io_queue_us += int64_t(ms_since(tq) * 1000.0);
                         auto tb = clk::now();
-                        if (!job->failed() && pwrite_all(fp->fd, slot, n, lo) != 0)
+                        static const bool dbg_skip_write = getenv("TSNAP_B200_DEBUG_SKIP_WRITE") != nullptr;  // experiments only
+                        if (!dbg_skip_write && !job->failed() && pwrite_all(fp->fd, slot, n, lo) != 0)
                             job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
                         job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
                         eng->ring.release(slot);
@@ -749,7 +748,7 @@ static int run_load_inner(tsnap_job* job) {
     rc = build_waves(job);
     if (rc != TSNAP_OK) return rc;
     for (Wave& w : job->waves) {
-        rc = plan_wave(job, w, false);
+        rc = plan_wave(job, w);
         if (rc != TSNAP_OK) return rc;
     }
     job->stats.plan_ms = ms_since(t0);
@@ -889,7 +888,7 @@ static int run_stage_inner(tsnap_job* job) {
     int rc = build_waves(job);
     if (rc != TSNAP_OK) return rc;
     Wave& w = job->waves[0];
-    rc = plan_wave(job, w, true);
+    rc = plan_wave(job, w);
     if (rc != TSNAP_OK) return rc;
     job->stats.plan_ms = ms_since(t0);
     if (job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));

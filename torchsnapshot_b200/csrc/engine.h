@@ -125,7 +125,6 @@ struct Wave {
     uint64_t region_off = 0;  // offset of the region inside the arena
     std::vector<Member> members;
     std::vector<Tile> tiles_bulk, tiles_lsu;
-    void* h_tables = nullptr;  // pinned staging of [members | bulk tiles | lsu tiles]
     void* d_tables = nullptr;
     size_t table_bytes = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr;  // kernel timing
