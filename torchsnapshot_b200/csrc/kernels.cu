@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -546,23 +547,64 @@ __global__ void __launch_bounds__(kLsuThreads, 3) tsnap_lsu_copy_kernel(const Me
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-constexpr int kBulkStages = 3;
-constexpr int kBulkStageBytes = 16 * 1024;
-constexpr int kBulkSmem = kBulkStages * kBulkStageBytes + kBulkStages * 8;
-constexpr int kBulkCtasPerSm = 4;
+// Ring geometry of the bulk kernel.  Default picked by measurement on B200 (profiles/r01_ncu_summary.md);
+// TSNAP_B200_BULK_CFG selects an alternative for A/B runs.
+struct BulkCfg {
+    int stages, stage_bytes, ctas_per_sm;
+};
+static const BulkCfg kBulkCfgs[] = {
+    {3, 16384, 4},  // 0: default — 48 KiB per CTA, 192 KiB per SM
+    {4, 8192, 6},   // 1
+    {2, 32768, 3},  // 2
+    {4, 16384, 3},  // 3
+    {6, 8192, 4},   // 4
+    {3, 32768, 2},  // 5
+};
+static int bulk_cfg_index() {
+    static const int idx = [] {
+        const char* e = getenv("TSNAP_B200_BULK_CFG");
+        const int n = int(sizeof(kBulkCfgs) / sizeof(kBulkCfgs[0]));
+        const int v = e ? atoi(e) : 0;
+        return v >= 0 && v < n ? v : 0;
+    }();
+    return idx;
+}
+
+template <int S, int B>
+static cudaError_t bulk_attr() {
+    return cudaFuncSetAttribute(tsnap_bulk_copy_kernel<S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * B + S * 8);
+}
+template <int S, int B>
+static void bulk_launch(const Member* m, const Tile* t, uint32_t n, uint32_t grid, cudaStream_t st) {
+    tsnap_bulk_copy_kernel<S, B><<<grid, 32, S * B + S * 8, st>>>(m, t, n);
+}
+
 constexpr int kLsuCtasPerSm = 6;
 
 cudaError_t init_kernels() {
-    return cudaFuncSetAttribute(tsnap_bulk_copy_kernel<kBulkStages, kBulkStageBytes>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem);
+    cudaError_t e = bulk_attr<3, 16384>();
+    if (e == cudaSuccess) e = bulk_attr<4, 8192>();
+    if (e == cudaSuccess) e = bulk_attr<2, 32768>();
+    if (e == cudaSuccess) e = bulk_attr<4, 16384>();
+    if (e == cudaSuccess) e = bulk_attr<6, 8192>();
+    if (e == cudaSuccess) e = bulk_attr<3, 32768>();
+    return e;
 }
 
 cudaError_t launch_bulk(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
                         cudaStream_t stream) {
     if (ntiles == 0) return cudaSuccess;
-    uint32_t grid = (uint32_t)sm_count * kBulkCtasPerSm;
+    const int ci = bulk_cfg_index();
+    uint32_t grid = (uint32_t)sm_count * kBulkCfgs[ci].ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
-    tsnap_bulk_copy_kernel<kBulkStages, kBulkStageBytes><<<grid, 32, kBulkSmem, stream>>>(d_members, d_tiles, ntiles);
+    switch (ci) {
+        case 1: bulk_launch<4, 8192>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 2: bulk_launch<2, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 3: bulk_launch<4, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 4: bulk_launch<6, 8192>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 5: bulk_launch<3, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
+        default: bulk_launch<3, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
+    }
     return cudaGetLastError();
 }
 
