@@ -60,7 +60,7 @@ def test_planner_tile_cover_and_classification():
 
     base = 1 << 33
     info = N.plan_describe([dev_desc(1 << 20, N.F32, base, 0)])  # 4 MiB dense aligned -> bulk
-    assert info["n_members_bulk"] == 1 and info["n_tiles_bulk"] == 64 and info["n_tiles_lsu"] == 0
+    assert info["n_members_bulk"] == 1 and info["n_tiles_bulk"] == 22 and info["n_tiles_lsu"] == 0
     info = N.plan_describe([dev_desc((1 << 20) + 3, N.U8, base, 0)])  # bulk body + 3-byte tail
     assert info["n_members_bulk"] == 1 and info["n_members_lsu"] == 1 and info["bytes_lsu"] == 3
     info = N.plan_describe([dev_desc(1 << 20, N.F32, base, 3)])  # destination misaligned -> LSU contig

@@ -553,19 +553,23 @@ struct BulkCfg {
     int stages, stage_bytes, ctas_per_sm;
 };
 static const BulkCfg kBulkCfgs[] = {
-    {3, 16384, 4},  // 0: default — 48 KiB per CTA, 192 KiB per SM
+    {3, 16384, 4},  // 0: first version — 48 KiB per CTA, 192 KiB per SM (0.95 of the measured copy peak)
     {4, 8192, 6},   // 1
     {2, 32768, 3},  // 2
     {4, 16384, 3},  // 3
     {6, 8192, 4},   // 4
     {3, 32768, 2},  // 5
+    {2, 49152, 2},  // 6: default — two 48 KiB stages per CTA, two CTAs per SM (0.98)
+    {3, 24576, 3},  // 7
+    {2, 65536, 1},  // 8
+    {4, 32768, 1},  // 9
 };
 static int bulk_cfg_index() {
     static const int idx = [] {
         const char* e = getenv("TSNAP_B200_BULK_CFG");
         const int n = int(sizeof(kBulkCfgs) / sizeof(kBulkCfgs[0]));
-        const int v = e ? atoi(e) : 0;
-        return v >= 0 && v < n ? v : 0;
+        const int v = e ? atoi(e) : 6;
+        return v >= 0 && v < n ? v : 6;
     }();
     return idx;
 }
@@ -588,6 +592,10 @@ cudaError_t init_kernels() {
     if (e == cudaSuccess) e = bulk_attr<4, 16384>();
     if (e == cudaSuccess) e = bulk_attr<6, 8192>();
     if (e == cudaSuccess) e = bulk_attr<3, 32768>();
+    if (e == cudaSuccess) e = bulk_attr<2, 49152>();
+    if (e == cudaSuccess) e = bulk_attr<3, 24576>();
+    if (e == cudaSuccess) e = bulk_attr<2, 65536>();
+    if (e == cudaSuccess) e = bulk_attr<4, 32768>();
     return e;
 }
 
@@ -603,7 +611,11 @@ cudaError_t launch_bulk(const Member* d_members, const Tile* d_tiles, uint32_t n
         case 3: bulk_launch<4, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
         case 4: bulk_launch<6, 8192>(d_members, d_tiles, ntiles, grid, stream); break;
         case 5: bulk_launch<3, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
-        default: bulk_launch<3, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 7: bulk_launch<3, 24576>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 8: bulk_launch<2, 65536>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 9: bulk_launch<4, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
+        case 0: bulk_launch<3, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
+        default: bulk_launch<2, 49152>(d_members, d_tiles, ntiles, grid, stream); break;
     }
     return cudaGetLastError();
 }
