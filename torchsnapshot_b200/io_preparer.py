@@ -49,12 +49,13 @@ class PrimitivePreparer:
         return type(obj).__name__ in PrimitiveEntry.supported_types
 
     @staticmethod
-    def prepare_write(obj: Any) -> PrimitiveEntry:
-        return PrimitiveEntry.from_object(obj)
-
-    @staticmethod
-    def prepare_read(entry: PrimitiveEntry) -> Tuple[List[ReadReq], Future[Any]]:
-        return [], Future(obj=entry.get_value())
+    def _tensor_like_writer(obj: Any):
+    """Preparer for tensor-like leaves, None for anything else."""
+    if isinstance(obj, ShardedTensor):
+        return ShardedTensorIOPreparer.prepare_write
+    if isinstance(obj, DTensor):
+        return DTensorIOPreparer.prepare_write
+    return None
 
 
 def prepare_write(
@@ -65,23 +66,24 @@ def prepare_write(
     is_async_snapshot: bool = False,
     _tensor_prepare_func: Optional[PrepareFunc] = None,
 ) -> Tuple[Entry, List[WriteReq]]:
+    """Leaf -> (manifest entry, write requests).  Primitives are inlined in the metadata; sharded leaves keep
+    their own replication bookkeeping (per-shard entries), everything else is flagged here (T:io_preparer.py:82-147)."""
     if PrimitivePreparer.should_inline(obj):
-        entry = PrimitivePreparer.prepare_write(obj)
-        entry.replicated = replicated
-        return entry, []
+        inline = PrimitivePreparer.prepare_write(obj)
+        inline.replicated = replicated
+        return inline, []
     path = get_storage_path(obj, logical_path, rank, replicated)
-    if isinstance(obj, ShardedTensor):
-        return ShardedTensorIOPreparer.prepare_write(path, obj, is_async_snapshot, _tensor_prepare_func)
-    if isinstance(obj, DTensor):
-        return DTensorIOPreparer.prepare_write(path, obj, is_async_snapshot, _tensor_prepare_func)
-    if isinstance(obj, torch.Tensor):
-        if obj.numel() * obj.element_size() > get_max_chunk_size_bytes():
-            plan = ChunkedTensorIOPreparer.chunk_tensor(obj)
-            entry, reqs = ChunkedTensorIOPreparer.prepare_write(path, obj, plan, is_async_snapshot, _tensor_prepare_func)
-        else:
-            entry, reqs = TensorIOPreparer.prepare_write(path, obj, is_async_snapshot, _tensor_prepare_func)
-    else:
+    sharded_writer = _tensor_like_writer(obj)
+    if sharded_writer is not None:
+        return sharded_writer(path, obj, is_async_snapshot, _tensor_prepare_func)
+    if not isinstance(obj, torch.Tensor):
         entry, reqs = ObjectIOPreparer.prepare_write(path, obj)
+    elif obj.numel() * obj.element_size() > get_max_chunk_size_bytes():
+        entry, reqs = ChunkedTensorIOPreparer.prepare_write(
+            path, obj, ChunkedTensorIOPreparer.chunk_tensor(obj), is_async_snapshot, _tensor_prepare_func
+        )
+    else:
+        entry, reqs = TensorIOPreparer.prepare_write(path, obj, is_async_snapshot, _tensor_prepare_func)
     entry.replicated = replicated
     return entry, reqs
 
@@ -89,18 +91,19 @@ def prepare_write(
 def prepare_read(
     entry: Entry, obj_out: Optional[Any] = None, buffer_size_limit_bytes: Optional[int] = None
 ) -> Tuple[List[ReadReq], Future[Any]]:
-    if isinstance(entry, ShardedTensorEntry):
-        return ShardedTensorIOPreparer.prepare_read(entry, obj_out)
-    if isinstance(entry, ChunkedTensorEntry):
-        return ChunkedTensorIOPreparer.prepare_read(entry, obj_out, buffer_size_limit_bytes=buffer_size_limit_bytes)
-    if isinstance(entry, DTensorEntry):
-        return DTensorIOPreparer.prepare_read(entry, obj_out)
-    if isinstance(entry, TensorEntry):
-        return TensorIOPreparer.prepare_read(entry, obj_out, buffer_size_limit_bytes=buffer_size_limit_bytes)
-    if isinstance(entry, ObjectEntry):
-        return ObjectIOPreparer.prepare_read(entry, obj_out)
-    if isinstance(entry, PrimitiveEntry):
-        return PrimitivePreparer.prepare_read(entry)
+    """Manifest entry (+ optional in-place target) -> (read requests, future).  T:io_preparer.py:150-182."""
+    budgeted = {"buffer_size_limit_bytes": buffer_size_limit_bytes}
+    readers = (
+        (ShardedTensorEntry, lambda: ShardedTensorIOPreparer.prepare_read(entry, obj_out)),
+        (ChunkedTensorEntry, lambda: ChunkedTensorIOPreparer.prepare_read(entry, obj_out, **budgeted)),
+        (DTensorEntry, lambda: DTensorIOPreparer.prepare_read(entry, obj_out)),
+        (TensorEntry, lambda: TensorIOPreparer.prepare_read(entry, obj_out, **budgeted)),
+        (ObjectEntry, lambda: ObjectIOPreparer.prepare_read(entry, obj_out)),
+        (PrimitiveEntry, lambda: PrimitivePreparer.prepare_read(entry)),
+    )
+    for kind, make in readers:
+        if isinstance(entry, kind):
+            return make()
     raise Exception(f"Unsupported entry type: {entry} ({entry.type}).")
 
 
