@@ -49,7 +49,15 @@ class PrimitivePreparer:
         return type(obj).__name__ in PrimitiveEntry.supported_types
 
     @staticmethod
-    def _tensor_like_writer(obj: Any):
+    def prepare_write(obj: Any) -> PrimitiveEntry:
+        return PrimitiveEntry.from_object(obj)
+
+    @staticmethod
+    def prepare_read(entry: PrimitiveEntry) -> Tuple[List[ReadReq], Future[Any]]:
+        return [], Future(obj=entry.get_value())
+
+
+def _tensor_like_writer(obj: Any):
     """Preparer for tensor-like leaves, None for anything else."""
     if isinstance(obj, ShardedTensor):
         return ShardedTensorIOPreparer.prepare_write
