@@ -242,3 +242,22 @@ def test_large_throughput_smoke(N, engine, tmp_path):
     job.wait()
     job.destroy()
     assert torch.equal(out, t)
+
+
+def test_trim_releases_hbm_and_pinned_memory(N, tmp_path):
+    eng = N.Engine(device=0, io_threads=4, pinned_slot_bytes=4 << 20, pinned_slots=4)
+    try:
+        t = det_tensor((1 << 22,), torch.float32, 3).to("cuda:0")  # 16 MiB
+        for rep in range(2):
+            job = eng.save_job()
+            f = job.add_file(str(tmp_path / f"t{rep}"), t.numel() * 4)
+            job.add_member(f, N.save_desc(t, 0), t)
+            job.submit(torch.cuda.current_stream().cuda_stream)
+            job.wait()
+            job.destroy()
+            assert eng.stats()["hbm_arena_bytes"] >= t.numel() * 4
+            eng.trim()
+            assert eng.stats()["hbm_arena_bytes"] == 0
+            assert (tmp_path / f"t{rep}").read_bytes() == wire_bytes(t)
+    finally:
+        eng.close()

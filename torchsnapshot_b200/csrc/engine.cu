@@ -260,6 +260,7 @@ bool tsnap_job::failed() {
 }
 void tsnap_job::part_done() {
     if (parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        eng->active_jobs.fetch_sub(1, std::memory_order_acq_rel);
         std::lock_guard<std::mutex> g(mu);
         stats.total_ms = ms_since(t_submit);
         if (!device_done) {
@@ -957,18 +958,44 @@ static void run_job(tsnap_job* job) {
     job->part_done();  // the drain thread's token: `job` may be destroyed by a waiter from here on
 }
 
+// Frees the staging arena.  Only the drain thread calls this, between jobs; the arena may still be the source
+// of in-flight D2H copies of the previous job, so both streams are drained first.
+static void free_arena(tsnap_engine* eng) {
+    if (!eng->arena) return;
+    // load jobs keep enqueueing uploads/scatters from the I/O workers after the drain thread moved on
+    while (eng->active_jobs.load(std::memory_order_acquire) > 0) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    cudaSetDevice(eng->device);
+    cudaStreamSynchronize(eng->s_kernel);
+    cudaStreamSynchronize(eng->s_copy);
+    cudaFree(eng->arena);
+    eng->arena = nullptr;
+    eng->arena_bytes = 0;
+}
+
 static void drain_main(tsnap_engine* eng) {
     bind_current_thread(eng->numa_cpus);
     for (;;) {
         tsnap_job* job = nullptr;
         {
             std::unique_lock<std::mutex> g(eng->q_mu);
-            eng->q_cv.wait(g, [eng] { return eng->stopping || !eng->job_q.empty(); });
+            eng->busy = false;
+            eng->q_cv.notify_all();
+            eng->q_cv.wait(g, [eng] { return eng->stopping || !eng->job_q.empty() || eng->trim_arena; });
+            if (eng->trim_arena && eng->job_q.empty()) {
+                g.unlock();
+                free_arena(eng);
+                g.lock();
+                eng->trim_arena = false;
+                eng->q_cv.notify_all();
+                continue;
+            }
             if (eng->job_q.empty()) return;
             job = eng->job_q.front();
             eng->job_q.pop_front();
+            eng->busy = true;
         }
         run_job(job);
+        if (eng->release_arena_after_job && eng->has_device) free_arena(eng);
     }
 }
 
@@ -1007,6 +1034,8 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
         eng->sm_count = prop.multiProcessorCount;
         eng->has_device = true;
         eng->numa_cpus = gpu_numa_cpus(cfg->device);
+        const char* rel = getenv("TSNAP_B200_RELEASE_ARENA");
+        eng->release_arena_after_job = rel && rel[0] == '1';
         eng->completion_thread = std::thread(completion_main, eng);
     }
     eng->io = new WorkerPool(cfg->io_threads > 0 ? cfg->io_threads : 16, eng->numa_cpus);
@@ -1017,6 +1046,13 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
 
 int tsnap_engine_trim(tsnap_engine* eng) {
     if (!eng) return set_err(TSNAP_EINVAL, "null engine");
+    if (eng->has_device) {
+        // the arena belongs to the drain thread: ask it to free it once it is idle, and wait for that
+        std::unique_lock<std::mutex> g(eng->q_mu);
+        eng->trim_arena = true;
+        eng->q_cv.notify_all();
+        eng->q_cv.wait(g, [eng] { return !eng->trim_arena || eng->stopping; });
+    }
     std::lock_guard<std::mutex> g(eng->pin_mu);
     for (auto& kv : eng->pin_cache) {
         if (eng->has_device) cudaFreeHost(kv.second);
@@ -1181,6 +1217,7 @@ static int submit(tsnap_job* job, void* stream, bool is_consumer) {
     if (is_consumer) job->consumer_stream = stream;
     job->submitted = true;
     job->t_submit = clk::now();
+    eng->active_jobs.fetch_add(1, std::memory_order_acq_rel);
     {
         std::lock_guard<std::mutex> g(eng->q_mu);
         eng->job_q.push_back(job);

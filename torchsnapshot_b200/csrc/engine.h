@@ -89,12 +89,16 @@ struct tsnap_engine {
     std::condition_variable c_cv;
     std::deque<Pending> pending;
     bool stopping = false;
+    bool trim_arena = false;    // drain thread frees the HBM arena when it is idle
+    bool busy = false;          // a job is being issued by the drain thread
+    bool release_arena_after_job = false;  // TSNAP_B200_RELEASE_ARENA=1
     // event pool
     std::mutex ev_mu;
     std::vector<cudaEvent_t> ev_free;
     cudaEvent_t get_event();
     void put_event(cudaEvent_t e);
     // stats
+    std::atomic<int> active_jobs{0};  // submitted and not yet complete
     std::atomic<uint64_t> kernels_launched{0}, bytes_d2h{0}, bytes_h2d{0}, bytes_written{0}, bytes_read{0};
 };
 
