@@ -41,13 +41,13 @@ def random_view(rng: random.Random, seed: int, dev: str) -> torch.Tensor:
     return t
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
 def test_random_slabs_pack_and_scatter(seed):
     from torchsnapshot_b200 import _native as N
 
     rng = random.Random(seed)
     eng = N.get_engine(0)
-    views = [random_view(rng, 1000 * seed + i, DEV) for i in range(120)]
+    views = [random_view(rng, 1000 * seed + i, DEV) for i in range(90)]
     off, descs, want = rng.choice([0, 0, 1, 3, 8]), [], []
     pad = off
     for v in views:
