@@ -251,3 +251,21 @@ def test_async_take_overlaps_with_compute(tmp_path):
     snap.restore({"m": tgt})
     for k in want:
         assert torch.equal(want[k], tgt[k]), k
+
+
+def test_back_to_back_async_takes_do_not_interfere(tmp_path):
+    # two snapshots in flight at once: the second must not reuse the staging arena before the first has drained
+    a = {f"a{i}": torch.randn(1 << 20, device=DEV) for i in range(48)}  # ~200 MB
+    b = {f"b{i}": torch.randn(1 << 20, device=DEV) for i in range(48)}
+    want_a = {k: v.clone() for k, v in a.items()}
+    want_b = {k: v.clone() for k, v in b.items()}
+    p1 = B.Snapshot.async_take(str(tmp_path / "s1"), {"m": B.StateDict(**a)})
+    p2 = B.Snapshot.async_take(str(tmp_path / "s2"), {"m": B.StateDict(**b)})
+    for v in list(a.values()) + list(b.values()):
+        v.zero_()
+    s1, s2 = p1.wait(), p2.wait()
+    for snap, want in ((s1, want_a), (s2, want_b)):
+        tgt = B.StateDict(**{k: torch.empty_like(v) for k, v in want.items()})
+        snap.restore({"m": tgt})
+        for k in want:
+            assert torch.equal(want[k], tgt[k]), k

@@ -260,6 +260,13 @@ bool tsnap_job::failed() {
 }
 void tsnap_job::part_done() {
     if (parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        if (holds_arena) {
+            {
+                std::lock_guard<std::mutex> ga(eng->arena_mu);
+                eng->arena_in_use = false;
+            }
+            eng->arena_cv.notify_all();
+        }
         eng->active_jobs.fetch_sub(1, std::memory_order_acq_rel);
         std::lock_guard<std::mutex> g(mu);
         stats.total_ms = ms_since(t_submit);
@@ -938,6 +945,16 @@ static int run_stage_inner(tsnap_job* job) {
 static void run_job(tsnap_job* job) {
     tsnap_engine* eng = job->eng;
     if (eng->has_device) cudaSetDevice(eng->device);
+    // Jobs are issued back to back, but the staging arena (and its two wave regions) belongs to one device job
+    // at a time: a job that touches the GPU waits here until its predecessor has completely drained.
+    bool device_job = job->kind == kStage;
+    for (const FileSpec& f : job->files) device_job = device_job || (!f.host_only && f.nbytes > 0);
+    if (device_job && eng->has_device) {
+        std::unique_lock<std::mutex> ga(eng->arena_mu);
+        eng->arena_cv.wait(ga, [eng] { return !eng->arena_in_use; });
+        eng->arena_in_use = true;
+        job->holds_arena = true;
+    }
     int rc;
     if (job->kind == kSave) rc = run_save_inner(job);
     else if (job->kind == kLoad) rc = run_load_inner(job);

@@ -73,6 +73,10 @@ struct tsnap_engine {
     // HBM staging arena (grow-only between jobs)
     char* arena = nullptr;
     size_t arena_bytes = 0;
+    // the arena serves one device job at a time: the next one waits until the previous has fully completed
+    std::mutex arena_mu;
+    std::condition_variable arena_cv;
+    bool arena_in_use = false;
     // cached whole-buffer pinned allocations for the stager seam, keyed by capacity
     std::mutex pin_mu;
     std::vector<std::pair<size_t, void*>> pin_cache;
@@ -150,6 +154,7 @@ struct tsnap_job {
     cudaEvent_t ev_copy_begin = nullptr, ev_copy_end = nullptr;  // timing of the payload D2H span
     void* consumer_stream = nullptr;
     bool submitted = false;
+    bool holds_arena = false;  // released in part_done when the job completes
     bool accounted = false;  // parts_left (incl. the drain thread's own token) has been set
     // completion state
     std::mutex mu;
