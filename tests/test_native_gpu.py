@@ -261,3 +261,19 @@ def test_trim_releases_hbm_and_pinned_memory(N, tmp_path):
             assert (tmp_path / f"t{rep}").read_bytes() == wire_bytes(t)
     finally:
         eng.close()
+
+
+def test_column_shard_throughput_smoke(N, engine):
+    # column-wise shard (narrow on dim 1): rows of 512 B inside 1 KiB-pitched storage -> STRIDED mode, 16 B granules
+    base = torch.empty(1 << 20, 256, dtype=torch.float32, device="cuda:0").uniform_()  # 1 GiB
+    view = base[:, 64:192]  # 512 MiB payload
+    n = view.numel() * 4
+    for _ in range(2):
+        sb = engine.stage([N.save_desc(view, 0)], n, stream=torch.cuda.current_stream().cuda_stream, keepalive=[base])
+        mv = sb.wait()
+        st = sb.stats()
+        got = torch.frombuffer(mv, dtype=torch.float32).reshape(view.shape).clone()
+        del mv
+        sb.release()
+    print("column shard stats", {k: st[k] for k in ("kernel_lsu_ms", "n_tiles_lsu")}, "GB/s", 2 * n / 1e9 / (st["kernel_lsu_ms"] / 1e3))
+    assert torch.equal(got, view.cpu())

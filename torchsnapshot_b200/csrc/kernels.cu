@@ -360,27 +360,53 @@ __device__ __forceinline__ void outer_offsets(const Member& m, uint64_t row, int
     *dofs = d;
 }
 
+// row index -> byte offsets on both sides; the single-outer-dim case (2-D narrow / column shard) needs no division
+__device__ __forceinline__ void row_offsets(const Member& m, uint64_t row, int64_t* so, int64_t* dofs) {
+    if (m.nouter == 1) {
+        *so = (int64_t)row * m.sstride[0];
+        *dofs = (int64_t)row * m.dstride[0];
+    } else {
+        outer_offsets(m, row, so, dofs);
+    }
+}
+
+// One granule (sizeof(T) bytes) per thread and step; kU independent loads are issued before the stores so that
+// several requests per thread are in flight (the address arithmetic would otherwise serialise load->store).
 template <typename T>
 __device__ __forceinline__ void tile_strided_t(const Member& m, uint64_t lo, uint64_t hi) {
+    constexpr int kU = sizeof(T) >= 16 ? 2 : 4;
     const char* sb = reinterpret_cast<const char*>(m.src);
     char* db = reinterpret_cast<char*>(m.dst);
     const uint64_t inner = m.inner;
     const bool small = ((m.bytes >> 32) == 0);
-    for (uint64_t pos = lo + (uint64_t)threadIdx.x * sizeof(T); pos < hi; pos += (uint64_t)kLsuThreads * sizeof(T)) {
-        uint64_t row, col;
-        if (small) {
-            const uint32_t p = (uint32_t)pos, in = (uint32_t)inner;
-            const uint32_t r = p / in;
-            row = r;
-            col = p - r * in;
-        } else {
-            row = pos / inner;
-            col = pos - row * inner;
+    const uint64_t stride = (uint64_t)kLsuThreads * sizeof(T);
+    for (uint64_t base = lo + (uint64_t)threadIdx.x * sizeof(T); base < hi; base += stride * kU) {
+        T v[kU];
+        int64_t dst_off[kU];
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+            const uint64_t pos = base + (uint64_t)k * stride;
+            dst_off[k] = -1;
+            if (pos < hi) {
+                uint64_t row, col;
+                if (small) {
+                    const uint32_t p = (uint32_t)pos, in = (uint32_t)inner;
+                    const uint32_t r = p / in;
+                    row = r;
+                    col = p - r * in;
+                } else {
+                    row = pos / inner;
+                    col = pos - row * inner;
+                }
+                int64_t so, dofs;
+                row_offsets(m, row, &so, &dofs);
+                v[k] = __ldg(reinterpret_cast<const T*>(sb + so + col));
+                dst_off[k] = dofs + (int64_t)col;
+            }
         }
-        int64_t so, dofs;
-        outer_offsets(m, row, &so, &dofs);
-        const T v = __ldg(reinterpret_cast<const T*>(sb + so + col));
-        *reinterpret_cast<T*>(db + dofs + col) = v;
+#pragma unroll
+        for (int k = 0; k < kU; ++k)
+            if (dst_off[k] >= 0) *reinterpret_cast<T*>(db + dst_off[k]) = v[k];
     }
 }
 
