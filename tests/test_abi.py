@@ -64,7 +64,7 @@ def test_planner_tile_cover_and_classification():
     info = N.plan_describe([dev_desc((1 << 20) + 3, N.U8, base, 0)])  # bulk body + 3-byte tail
     assert info["n_members_bulk"] == 1 and info["n_members_lsu"] == 1 and info["bytes_lsu"] == 3
     info = N.plan_describe([dev_desc(1 << 20, N.F32, base, 3)])  # destination misaligned -> LSU contig
-    assert info["n_members_bulk"] == 0 and info["n_tiles_lsu"] == 129
+    assert info["n_members_bulk"] == 0 and info["n_tiles_lsu"] == 33
     info = N.plan_describe([dev_desc(100, N.F32, base, 0)])  # too small for the bulk engine
     assert info["n_members_bulk"] == 0 and info["n_tiles_lsu"] == 1
     # strided 2-D view

@@ -371,37 +371,48 @@ __device__ __forceinline__ void row_offsets(const Member& m, uint64_t row, int64
 }
 
 // One granule (sizeof(T) bytes) per thread and step; kU independent loads are issued before the stores so that
-// several requests per thread are in flight (the address arithmetic would otherwise serialise load->store).
+// several requests per thread are in flight.  (row, col) of a thread's granule is divided out once per tile and
+// then advanced incrementally: consecutive granules of a thread are a constant number of bytes apart.
 template <typename T>
 __device__ __forceinline__ void tile_strided_t(const Member& m, uint64_t lo, uint64_t hi) {
-    constexpr int kU = sizeof(T) >= 16 ? 2 : 4;
+    constexpr int kU = sizeof(T) >= 8 ? 4 : 8;  // bytes in flight per SM = 3 CTAs x 256 thr x kU x sizeof(T)
     const char* sb = reinterpret_cast<const char*>(m.src);
     char* db = reinterpret_cast<char*>(m.dst);
     const uint64_t inner = m.inner;
-    const bool small = ((m.bytes >> 32) == 0);
     const uint64_t stride = (uint64_t)kLsuThreads * sizeof(T);
-    for (uint64_t base = lo + (uint64_t)threadIdx.x * sizeof(T); base < hi; base += stride * kU) {
+    uint64_t pos = lo + (uint64_t)threadIdx.x * sizeof(T);
+    if (pos >= hi) return;
+    uint64_t row, col, drow, dcol;
+    if ((m.bytes >> 32) == 0) {
+        const uint32_t in = (uint32_t)inner;
+        row = (uint32_t)pos / in;
+        col = (uint32_t)pos - (uint32_t)row * in;
+        drow = (uint32_t)stride / in;
+        dcol = (uint32_t)stride - (uint32_t)drow * in;
+    } else {
+        row = pos / inner;
+        col = pos - row * inner;
+        drow = stride / inner;
+        dcol = stride - drow * inner;
+    }
+    while (pos < hi) {
         T v[kU];
         int64_t dst_off[kU];
 #pragma unroll
         for (int k = 0; k < kU; ++k) {
-            const uint64_t pos = base + (uint64_t)k * stride;
             dst_off[k] = -1;
             if (pos < hi) {
-                uint64_t row, col;
-                if (small) {
-                    const uint32_t p = (uint32_t)pos, in = (uint32_t)inner;
-                    const uint32_t r = p / in;
-                    row = r;
-                    col = p - r * in;
-                } else {
-                    row = pos / inner;
-                    col = pos - row * inner;
-                }
                 int64_t so, dofs;
                 row_offsets(m, row, &so, &dofs);
-                v[k] = __ldg(reinterpret_cast<const T*>(sb + so + col));
+                v[k] = __ldg(reinterpret_cast<const T*>(sb + so + (int64_t)col));
                 dst_off[k] = dofs + (int64_t)col;
+            }
+            pos += stride;
+            row += drow;
+            col += dcol;
+            if (col >= inner) {
+                col -= inner;
+                ++row;
             }
         }
 #pragma unroll

@@ -18,7 +18,7 @@ namespace tsnap {
 
 constexpr int kMaxOuter = 8;
 constexpr uint32_t kTileBulk = 192 * 1024;  // bytes of one bulk (TMA) tile: a multiple of every ring stage size
-constexpr uint32_t kTileLsu = 32 * 1024;   // logical dst bytes of one LSU tile
+constexpr uint32_t kTileLsu = 128 * 1024;  // logical dst bytes of one LSU tile (per-tile setup costs ~2 dependent global round trips)
 constexpr uint64_t kBulkMin = 1024;        // contiguous runs shorter than this stay on the LSU path
 
 enum Mode : uint32_t {
