@@ -11,6 +11,11 @@ import struct
 from dataclasses import asdict, dataclass, field
 from typing import Any, ClassVar, Dict, List, Optional, Tuple, Union
 
+try:  # the YAML fallback reader; same loader preference as the reference (T:manifest.py:22-25)
+    from yaml import CSafeLoader as Loader
+except ImportError:  # pragma: no cover
+    from yaml import SafeLoader as Loader
+
 SNAPSHOT_FORMAT_VERSION = "0.1.0"  # value the reference writes into "version" (T:version.py)
 
 
@@ -221,13 +226,14 @@ class SnapshotMetadata:
         return json.dumps(asdict(self), sort_keys=False, indent=2)
 
     @classmethod
-    def from_yaml(cls, text: str) -> "SnapshotMetadata":
+    def from_yaml(cls, yaml_str: str) -> "SnapshotMetadata":
+        text = yaml_str
         try:
             d = json.loads(text)
         except ValueError:
             import yaml  # snapshots from very old writers are real YAML
 
-            d = yaml.safe_load(text)
+            d = yaml.load(text, Loader=Loader)
         manifest: Manifest = {}
         for path, obj in d["manifest"].items():
             e = entry_from_yaml_obj(obj)

@@ -128,11 +128,20 @@ def describe_consumer(c: Any) -> Optional[Described]:
     return _describe_tensor_consumer(c, 0)
 
 
-def native_root(storage: Any) -> Optional[str]:
-    """Root directory when `storage` is a plain local-filesystem plugin the engine can write for."""
+def native_root(storage: Any, op: str = "write") -> Optional[str]:
+    """Root directory when `storage` is a plain local-filesystem plugin the engine may do the I/O for.
+
+    A subclass that overrides ``write`` / ``read`` (fault injection, throttling, auditing …) keeps control of that
+    operation: the engine only takes over when the method is the stock one."""
+    cls = type(storage)
     root = getattr(storage, "native_root", None)
     if root is not None:
+        from .storage_plugins.fs import FSStoragePlugin
+
+        stock = getattr(FSStoragePlugin, op, None)
+        if isinstance(storage, FSStoragePlugin) and getattr(cls, op, None) is not stock:
+            return None
         return root
-    if type(storage).__name__ == "FSStoragePlugin" and isinstance(getattr(storage, "root", None), str):
+    if cls.__name__ == "FSStoragePlugin" and cls.__module__.endswith("storage_plugins.fs") and isinstance(getattr(storage, "root", None), str):
         return storage.root
     return None

@@ -174,3 +174,10 @@ def consolidate_replicated_entries(rank_to_entries: List[Dict[str, Entry]], dedu
             continue
         entries.update(shared)
     return rank_to_entries
+
+
+def consolidate_replicated_entries_dist(entries: Dict[str, Entry], pg: PGWrapper, dedup: bool = True) -> Dict[str, Entry]:
+    """Collective form of :func:`consolidate_replicated_entries` (T:partitioner.py:358-368)."""
+    gathered: List[Dict[str, Entry]] = [None] * pg.get_world_size()  # type: ignore[list-item]
+    pg.all_gather_object(gathered, entries)
+    return consolidate_replicated_entries(gathered, dedup=dedup)[pg.get_rank()]

@@ -34,3 +34,25 @@ class PGWrapper:
             obj_list[0] = obj
         else:
             dist.all_gather_object(obj_list, obj, group=self.pg)
+
+    def scatter_object_list(self, output_list: List[Any], input_list: Optional[List[Any]], src: int = 0) -> None:
+        """output_list[0] <- input_list[rank] of rank `src` (T:pg_wrapper.py:60-91; NCCL has no object scatter, so
+        it is emulated with a broadcast there)."""
+        rank, world = self.get_rank(), self.get_world_size()
+        if rank == src:
+            if input_list is None:
+                raise RuntimeError("The src rank's input_list for scatter_object_list must not be None.")
+            if len(input_list) != world:
+                raise RuntimeError(
+                    f"The length of input_list {len(input_list)} for scatter_object_list "
+                    f"must be the same as the process group's world size ({world})."
+                )
+        if self.pg is None:
+            output_list[0] = input_list[0]  # type: ignore[index]
+            return
+        if dist.get_backend(self.pg) == "nccl":
+            payload = list(input_list) if rank == src else [None] * world
+            self.broadcast_object_list(payload, src=src)
+            output_list[0] = payload[rank]
+            return
+        dist.scatter_object_list(output_list, input_list if rank == src else None, src=dist.get_global_rank(self.pg, src), group=self.pg)

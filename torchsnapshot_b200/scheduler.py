@@ -153,7 +153,7 @@ async def execute_write_reqs(
         t_mark[0] = now
 
     loop = asyncio.get_running_loop()
-    root = _native_root(storage)
+    root = _native_root(storage, "write")
     native: Optional[_NativeJobs] = None
     generic: List[WriteReq] = []
     total = 0
@@ -240,7 +240,7 @@ def sync_execute_write_reqs(
 async def execute_read_reqs(read_reqs: List[ReadReq], storage: StoragePlugin, memory_budget_bytes: int, rank: int) -> None:
     begin = time.monotonic()
     loop = asyncio.get_running_loop()
-    root = _native_root(storage)
+    root = _native_root(storage, "read")
     native: Optional[_NativeJobs] = None
     generic: List[ReadReq] = []
     total = 0

@@ -115,3 +115,69 @@ def torch_save_as_bytes(obj) -> bytes:
 
 def torch_load_from_bytes(buf):
     return torch.load(io.BytesIO(buf), weights_only=False)
+
+
+# ---- quantized tensors: the reference's self-describing formats (T:serialization.py:278-477) ---------------
+# Specified and unit-tested by the reference but not wired into any of its preparers (quantized tensors travel
+# as torch.save pickles); kept here with the same names so that either side can adopt them later.
+#
+#   per-tensor : [ int_repr bytes, C order ][ q_scale: C double ][ q_zero_point: C long long ]
+#   per-channel: [ axis: C long long ][ int_repr bytes, C order ][ scales: float64 x shape[axis] ][ zero_points: int64 x shape[axis] ]
+import struct as _struct
+
+_INT_REPR = {torch.qint8: torch.int8, torch.quint8: torch.uint8, torch.qint32: torch.int32}
+
+
+def _int_repr_bytes(tensor: torch.Tensor) -> bytes:
+    return bytes(tensor_as_memoryview(tensor.contiguous().int_repr()))
+
+
+def _int_repr_from(buf: memoryview, dtype: torch.dtype, shape: List[int]) -> torch.Tensor:
+    return tensor_from_memoryview(buf, dtype=_INT_REPR[dtype], shape=shape)
+
+
+def per_tensor_qtensor_as_bytes(tensor: torch.Tensor) -> bytes:
+    if not tensor.is_quantized or tensor.qscheme() != torch.per_tensor_affine:
+        raise RuntimeError("per_tensor_qtensor_as_bytes() only supports per_tensor_affine quantized tensor.")
+    return _int_repr_bytes(tensor) + _struct.pack("d", tensor.q_scale()) + _struct.pack("q", tensor.q_zero_point())
+
+
+def per_tensor_qtensor_from_bytes(buf: bytes, dtype: torch.dtype, shape: List[int]) -> torch.Tensor:
+    view = memoryview(buf)
+    body = len(view) - 16
+    expected = dtype_to_element_size(dtype)
+    for s in shape:
+        expected *= s
+    if body != expected:
+        raise RuntimeError(f"The size of the buffer ({len(view)}) does not match the dtype/shape ({expected} + 16).")
+    (scale,) = _struct.unpack("d", view[body : body + 8])
+    (zero_point,) = _struct.unpack("q", view[body + 8 : body + 16])
+    return torch._make_per_tensor_quantized_tensor(_int_repr_from(view[:body], dtype, shape), scale, zero_point)
+
+
+def per_channel_qtensor_as_bytes(tensor: torch.Tensor) -> bytes:
+    if not tensor.is_quantized or tensor.qscheme() not in (torch.per_channel_affine, torch.per_channel_affine_float_qparams):
+        raise RuntimeError("per_channel_qtensor_as_bytes() only supports per_channel_affine quantized tensor.")
+    scales = tensor.q_per_channel_scales().to(torch.float64)
+    zero_points = tensor.q_per_channel_zero_points().to(torch.int64)
+    return (
+        _struct.pack("q", tensor.q_per_channel_axis())
+        + _int_repr_bytes(tensor)
+        + bytes(tensor_as_memoryview(scales))
+        + bytes(tensor_as_memoryview(zero_points))
+    )
+
+
+def per_channel_qtensor_from_bytes(buf: bytes, dtype: torch.dtype, shape: List[int]) -> torch.Tensor:
+    view = memoryview(buf)
+    (axis,) = _struct.unpack("q", view[:8])
+    body = dtype_to_element_size(dtype)
+    for s in shape:
+        body *= s
+    channels = shape[axis]
+    if len(view) != 8 + body + 16 * channels:
+        raise RuntimeError(f"The size of the buffer ({len(view)}) does not match the dtype/shape/axis.")
+    ints = _int_repr_from(view[8 : 8 + body], dtype, shape)
+    scales = tensor_from_memoryview(view[8 + body : 8 + body + 8 * channels], dtype=torch.float64, shape=[channels])
+    zero_points = tensor_from_memoryview(view[8 + body + 8 * channels :], dtype=torch.int64, shape=[channels])
+    return torch._make_per_channel_quantized_tensor(ints, scales, zero_points, axis)

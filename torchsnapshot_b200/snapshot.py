@@ -377,7 +377,12 @@ class Snapshot:
         globs = cls._infer_replicated(replicated, app_state)
         everyone: List[Any] = [None] * pgw.get_world_size()
         pgw.all_gather_object(everyone, globs)
-        return box[0], set.intersection(*map(set, everyone))
+        return box[0], cls._coalesce_replicated(everyone)
+
+    @staticmethod
+    def _coalesce_replicated(global_replicated: List[List[str]]) -> Set[str]:
+        """Only globs that every rank specified count (T:snapshot.py:914-918)."""
+        return set.intersection(*map(set, global_replicated))
 
     @staticmethod
     def _infer_replicated(replicated: List[str], app_state: AppState) -> List[str]:
