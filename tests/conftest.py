@@ -21,3 +21,6 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+# tests/ref_suite holds the runner for the reference's own test files; it is driven by tests/test_reference_suite.py
+collect_ignore = ["ref_suite"]

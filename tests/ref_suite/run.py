@@ -72,7 +72,7 @@ if __name__ == "__main__":
     extra = [a for a in sys.argv[1:] if not a.endswith(".py") and a != "--fast"]
     for f in picked:
         os.symlink(os.path.join(REF_TESTS, f), os.path.join(work, f))
-    shutil.copy(os.path.join(HERE, "conftest.py"), os.path.join(work, "conftest.py"))
+    shutil.copy(os.path.join(HERE, "overlay_conftest.py"), os.path.join(work, "conftest.py"))
     os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
     sys.path.insert(0, work)
     os.environ["PYTHONPATH"] = work + os.pathsep + os.environ.get("PYTHONPATH", "")
