@@ -74,9 +74,13 @@ class _OverlappingRegion:
 
 
 class ShardedTensorBufferConsumer(BufferConsumer):
-    def __init__(self, overlapping_regions: List[_OverlappingRegion], entry: TensorEntry) -> None:
+    def __init__(self, overlapping_regions: List[_OverlappingRegion], entry: TensorEntry, wire_skip: int = 0, wire_len: Optional[int] = None) -> None:
         self.overlapping_regions = overlapping_regions
         self.entry = entry
+        # the buffer handed to this consumer starts `wire_skip` bytes into the saved piece and is `wire_len` bytes
+        # long (the hull of the bytes the regions need); 0 / None = the whole piece, as in the reference
+        self.wire_skip = wire_skip
+        self.wire_len = wire_len
 
     def is_raw(self) -> bool:
         if self.entry.serializer != RAW:
@@ -103,7 +107,7 @@ class ShardedTensorBufferConsumer(BufferConsumer):
                 first += so * strides[dim]
             if dst.numel() == 0:
                 continue
-            descs.append(_native.load_desc(dst, wire_offset + first * esz, wire_dtype=dtype, wire_strides=strides))
+            descs.append(_native.load_desc(dst, wire_offset + first * esz - self.wire_skip, wire_dtype=dtype, wire_strides=strides))
             keep.append(region.dst_tensor)
         return descs, keep
 
@@ -114,6 +118,8 @@ class ShardedTensorBufferConsumer(BufferConsumer):
                 if descs:
                     engine_for(self.overlapping_regions[0].dst_tensor).consume(buf, descs)
                 return
+            if self.wire_skip or self.wire_len is not None:
+                raise AssertionError("partial reads are only planned for raw entries")
             saved = TensorBufferConsumer.deserialize_tensor(buf, self.entry)
             for region in self.overlapping_regions:
                 s, d = region.get_views(saved)
@@ -125,8 +131,36 @@ class ShardedTensorBufferConsumer(BufferConsumer):
             work()
 
     def get_consuming_cost_bytes(self) -> int:
-        n = entry_nbytes(self.entry)
+        n = entry_nbytes(self.entry) if self.wire_len is None else self.wire_len
         return 2 * n if self.entry.serializer == PICKLED else n
+
+
+def needed_hull(entry: TensorEntry, regions: List[_OverlappingRegion]) -> Optional[Tuple[int, int]]:
+    """Byte hull [lo, hi) inside the saved piece that the overlap regions touch, or None when the whole piece is
+    needed (or the piece is not a raw image).  The reference always reads whole pieces (T:io_preparers/
+    sharded_tensor.py:252-270: "read each persisted shard once"), which amplifies reads whenever a local shard only
+    needs a few rows of a 512 MiB piece; reading the hull is the cheap half of SURVEY.md's N3."""
+    if entry.serializer != RAW:
+        return None
+    shape = list(entry.shape)
+    esz = torch.empty(0, dtype=string_to_dtype(entry.dtype)).element_size()
+    strides = [1] * len(shape)
+    for i in range(len(shape) - 2, -1, -1):
+        strides[i] = strides[i + 1] * shape[i + 1]
+    lo, hi = None, None
+    for r in regions:
+        first = sum(so * strides[d] for d, so, _, _ in r.overlap_region)
+        last = first + sum((n - 1) * strides[d] for d, _, _, n in r.overlap_region)
+        lo = first if lo is None else min(lo, first)
+        hi = last + 1 if hi is None else max(hi, last + 1)
+    if lo is None:
+        return None
+    total = 1
+    for s_ in shape:
+        total *= s_
+    if lo == 0 and hi == total:
+        return None
+    return lo * esz, hi * esz
 
 
 def overlap_read_reqs(shards: List[Shard], local: List[Tuple[torch.Tensor, List[int], List[int]]]) -> List[ReadReq]:
@@ -138,14 +172,16 @@ def overlap_read_reqs(shards: List[Shard], local: List[Tuple[torch.Tensor, List[
             for t, off, sz in local
             if boxes_overlap(piece.offsets, piece.sizes, off, sz)
         ]
-        if regions:
-            reqs.append(
-                ReadReq(
-                    path=piece.tensor.location,
-                    buffer_consumer=ShardedTensorBufferConsumer(regions, piece.tensor),
-                    byte_range=piece.tensor.byte_range_tuple,
-                )
-            )
+        if not regions:
+            continue
+        consumer = ShardedTensorBufferConsumer(regions, piece.tensor)
+        byte_range = piece.tensor.byte_range_tuple
+        hull = needed_hull(piece.tensor, regions) if consumer.is_raw() else None
+        if hull is not None:
+            base = byte_range[0] if byte_range is not None else 0
+            consumer.wire_skip, consumer.wire_len = hull[0], hull[1] - hull[0]
+            byte_range = (base + hull[0], base + hull[1])
+        reqs.append(ReadReq(path=piece.tensor.location, buffer_consumer=consumer, byte_range=byte_range))
     return reqs
 
 

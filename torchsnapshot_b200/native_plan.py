@@ -89,6 +89,9 @@ def _describe_tensor_consumer(c: Any, offset: int) -> Optional[Described]:
         for i in range(len(shape) - 2, -1, -1):
             strides[i] = strides[i + 1] * shape[i + 1]
         descs, keep = [], []
+        skip = int(getattr(c, "wire_skip", 0) or 0)
+        if getattr(c, "wire_len", None) is not None:
+            nbytes = int(c.wire_len)
         for region in regions:
             dst = region.dst_tensor.detach()
             if not _castable(src_dtype, dst.dtype) or dst.is_quantized:
@@ -99,7 +102,7 @@ def _describe_tensor_consumer(c: Any, offset: int) -> Optional[Described]:
                 first += so * strides[dim]
             if dst.numel() == 0:
                 continue
-            descs.append(_native.load_desc(dst, offset + first * esz, wire_dtype=src_dtype, wire_strides=strides))
+            descs.append(_native.load_desc(dst, offset + first * esz - skip, wire_dtype=src_dtype, wire_strides=strides))
             keep.append(region.dst_tensor)
         return descs, keep, nbytes
     tensor = getattr(c, "tensor", None)
