@@ -517,7 +517,9 @@ static int64_t count_parts(tsnap_engine* eng, const FileSpec& f, bool save) {
     const uint64_t sb = eng->ring.slot_bytes();
     if (f.host_only) {
         Member m;
-        if (direct_host_member(f, save, &m)) return int64_t((f.nbytes + sb - 1) / sb);
+        // direct reads run in parallel parts (shared inode lock); direct writes of one file are one sequential
+        // part: buffered writes serialise on the inode lock anyway, parallel parts only add contention
+        if (!save && direct_host_member(f, save, &m)) return int64_t((f.nbytes + sb - 1) / sb);
         return 1;
     }
     return int64_t((f.nbytes + sb - 1) / sb);
@@ -532,6 +534,17 @@ static void post_host_file(tsnap_job* job, int fi, bool save) {
         return;
     }
     Member dm;
+    if (save && direct_host_member(f, save, &dm)) {
+        eng->io->post([job, &f, dm, sb] {
+            for (uint64_t lo = 0; lo < f.nbytes && !job->failed(); lo += sb) {
+                const uint64_t n = std::min<uint64_t>(sb, f.nbytes - lo);
+                if (pwrite_all(f.fd, reinterpret_cast<const char*>(uintptr_t(dm.src)) + lo, n, lo) != 0)
+                    job->fail(TSNAP_EIO, "pwrite " + f.path + ": " + strerror(errno));
+            }
+            finish_file_part(job, f, f.nbytes, true);
+        });
+        return;
+    }
     if (direct_host_member(f, save, &dm)) {
         for (uint64_t lo = 0; lo < f.nbytes; lo += sb) {
             const uint64_t n = std::min(sb, f.nbytes - lo);
