@@ -19,6 +19,14 @@ def random_view(rng: random.Random, seed: int, dev: str) -> torch.Tensor:
     shape = [rng.choice([1, 2, 3, 5, 8, 17, 32, 64, 129]) for _ in range(nd)]
     if rng.random() < 0.15:
         shape[rng.randrange(nd)] = rng.choice([1000, 4099, 16384])
+    while True:  # keep every base tensor below ~2M elements
+        numel = 1
+        for s_ in shape:
+            numel *= s_
+        if numel <= (1 << 21):
+            break
+        big = max(range(nd), key=lambda d: shape[d])
+        shape[big] = max(1, shape[big] // 2)
     t = det_tensor(tuple(shape), dt, seed).to(dev)
     if rng.random() < 0.5 and nd > 1:
         perm = list(range(nd))
