@@ -672,12 +672,10 @@ static int run_save_inner(tsnap_job* job) {
         if (launched == nw) arm_device_done(w);
         return TSNAP_OK;
     };
-    int64_t posted_parts = 0;
     // host-only files go straight to the I/O workers
     for (size_t i = 0; i < job->files.size(); ++i) {
         FileSpec& f = job->files[i];
         if (f.host_only || f.nbytes == 0) {
-            posted_parts += f.parts_left.load();
             post_host_file(job, int(i), true);
         }
     }
@@ -719,7 +717,6 @@ static int run_save_inner(tsnap_job* job) {
                      cudaEventRecord(ev, eng->s_copy) == cudaSuccess;
                 if (!ok) job->fail(TSNAP_ECUDA, std::string("D2H copy: ") + cudaGetErrorString(cudaGetLastError()));
                 eng->bytes_d2h += n;
-                ++posted_parts;
                 FileSpec* fp = &f;
                 push_pending(eng, ev, [eng, job, fp, slot, lo, n, ev](bool evok) {
                     eng->put_event(ev);
