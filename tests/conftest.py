@@ -8,7 +8,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_native_library() -> None:
+    """The test-suite needs torchsnapshot_b200/lib/libtsnap_b200.so; build it (nvcc cross-compiles without a GPU) when
+    a fresh checkout has not run __graft_entry__.build() yet."""
+    lib = os.path.join(ROOT, "torchsnapshot_b200", "lib", "libtsnap_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(ROOT, "torchsnapshot_b200", "csrc")], check=True)
+
+
 def pytest_configure(config):
+    _ensure_native_library()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
