@@ -363,8 +363,15 @@ class RefPipeline:
             async with io_gate:
                 await loop.run_in_executor(io_pool, write_file, path, buf)
 
+        async def stage(t: torch.Tensor):
+            # CUDA tensors hop to the 4-thread pool for the D2H copy; CPU tensors are viewed in place on the loop
+            # thread (T:io_preparers/tensor.py:249-266)
+            if t.is_cuda:
+                return await loop.run_in_executor(stage_pool, to_cpu, t)
+            return to_cpu(t)
+
         async def single(loc: str) -> None:
-            buf = await loop.run_in_executor(stage_pool, to_cpu, by_loc[loc])
+            buf = await stage(by_loc[loc])
             await write(loc, buf)
 
         async def slab_task(k: int, slab) -> None:
@@ -379,7 +386,7 @@ class RefPipeline:
                 buf = memoryview(host.numpy())
             else:
                 blob = bytearray(size)
-                staged = await asyncio.gather(*[loop.run_in_executor(stage_pool, to_cpu, by_loc[loc]) for loc, _, _ in slab["members"]])
+                staged = await asyncio.gather(*[stage(by_loc[loc]) for loc, _, _ in slab["members"]])
                 for (loc, lo, hi), b in zip(slab["members"], staged):
                     blob[lo:hi] = b
                 buf = memoryview(blob)
