@@ -1,0 +1,124 @@
+"""Host-side planning logic against the oracle on random inputs (hypothesis): chunk plans, shard subdivision, slab
+assignment / relocation, greedy partitioning, overlap boxes, knobs."""
+import os
+
+import pytest
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import ref_port as R
+from torchsnapshot_b200 import knobs
+from torchsnapshot_b200.batcher import batch_write_requests
+from torchsnapshot_b200.io_preparers.chunked_tensor import ChunkedTensorIOPreparer
+from torchsnapshot_b200.io_preparers.sharded_tensor import ShardedTensorIOPreparer, boxes_overlap, overlap_narrows
+from torchsnapshot_b200.io_preparers.tensor import TensorIOPreparer
+from torchsnapshot_b200.partitioner import _partition_write_loads, _WriteLoad
+
+FAST = settings(max_examples=60, deadline=None)
+
+
+@FAST
+@given(st.lists(st.integers(1, 40), min_size=0, max_size=3), st.sampled_from([torch.uint8, torch.bfloat16, torch.float32, torch.float64]), st.integers(1, 5000))
+def test_chunk_plan_matches_oracle(shape, dtype, limit):
+    t = torch.zeros(shape, dtype=dtype)
+    if t.numel() == 0:
+        return
+    plan = ChunkedTensorIOPreparer.chunk_tensor(t, chunk_sz_bytes=limit)
+    assert [(c.offsets, c.sizes) for c in plan] == R.chunk_plan(shape, t.element_size(), limit)
+    # chunks tile the tensor along dim 0
+    rows = sum(c.sizes[0] for c in plan)
+    assert rows == (shape[0] if shape else 1)
+
+
+@FAST
+@given(st.lists(st.integers(1, 30), min_size=1, max_size=3), st.integers(0, 2), st.integers(1, 3000), st.sampled_from([1, 2, 4, 8]))
+def test_subdivide_matches_oracle(sizes, dim, limit, esz):
+    dim = dim % len(sizes)
+    dtype = {1: torch.uint8, 2: torch.int16, 4: torch.float32, 8: torch.float64}[esz]
+    shard = torch.zeros(sizes, dtype=dtype)
+    offsets = [3 * (i + 1) for i in range(len(sizes))]
+    got = ShardedTensorIOPreparer.subdivide_shard(shard, offsets, sizes, dim, limit)
+    want = R.subdivide_plan(offsets, sizes, dim, esz, limit)
+    assert [(o, s) for _, o, s in got] == [(o, s) for _, o, s in want]
+    assert sum(v.shape[dim] for v, _, _ in got) == sizes[dim]
+
+
+@FAST
+@given(st.lists(st.integers(1, 300), min_size=1, max_size=40), st.integers(16, 400))
+def test_slab_assignment_and_relocation_match_oracle(sizes, threshold):
+    entries, reqs = [], []
+    for i, n in enumerate(sizes):
+        e, w = TensorIOPreparer.prepare_write(f"0/t{i}", torch.zeros(n, dtype=torch.uint8))
+        entries.append(e)
+        reqs += w
+    order = [(f"0/t{i}", n, False, True) for i, n in enumerate(sizes)]
+    passthrough, slabs = R.slab_assign(order, threshold)
+    _, batched = batch_write_requests(entries, reqs, slab_size_threshold_bytes=threshold)
+    assert [w.path for w in batched if not w.path.startswith("batched/")] == passthrough
+    got_slabs = [w for w in batched if w.path.startswith("batched/")]
+    assert len(got_slabs) == len(slabs)
+    for w, s in zip(got_slabs, slabs):
+        assert list(w.buffer_stager.byte_range_to_buffer_stager.keys()) == [(lo, hi) for _, lo, hi in s["members"]]
+    where = {loc: (k, lo, hi) for k, s in enumerate(slabs) for loc, lo, hi in s["members"]}
+    for i, e in enumerate(entries):
+        if f"0/t{i}" in where:
+            k, lo, hi = where[f"0/t{i}"]
+            assert e.location == got_slabs[k].path and e.byte_range == [lo, hi]
+        else:
+            assert e.location == f"0/t{i}" and e.byte_range is None
+
+
+@FAST
+@given(st.lists(st.integers(1, 1000), min_size=1, max_size=30), st.lists(st.integers(0, 500), min_size=1, max_size=6))
+def test_greedy_partition_matches_oracle(sizes, initial_loads):
+    world = len(initial_loads)
+    from torchsnapshot_b200.manifest import TensorEntry
+
+    entries = {f"p{i}": TensorEntry(f"replicated/p{i}", "buffer_protocol", "torch.uint8", [n], True) for i, n in enumerate(sizes)}
+    loads = {f"p{i}": [_WriteLoad(f"p{i}", 0, n)] for i, n in enumerate(sizes)}
+    got = _partition_write_loads([entries] * world, [loads] * world, list(initial_loads), world)
+    want = R.partition_greedy([(f"p{i}", n) for i, n in enumerate(sizes)], initial_loads)
+    assert [[wl.logical_path for wl in r] for r in got] == want
+    # every path written exactly once
+    assert sorted(wl.logical_path for r in got for wl in r) == sorted(loads)
+
+
+@FAST
+@given(st.integers(1, 3), st.data())
+def test_overlap_boxes_match_oracle(nd, data):
+    def box():
+        off = [data.draw(st.integers(0, 20)) for _ in range(nd)]
+        sz = [data.draw(st.integers(1, 20)) for _ in range(nd)]
+        return off, sz
+
+    a, b = box(), box()
+    assert boxes_overlap(*a, *b) == R.boxes_overlap(*a, *b)
+    if R.boxes_overlap(*a, *b):
+        assert overlap_narrows(a, b) == R.overlap_region(a[0], a[1], b[0], b[1])
+        assert all(n > 0 for _, _, _, n in overlap_narrows(a, b))
+
+
+def test_knobs_follow_the_reference_environment_variables(monkeypatch):
+    for env, getter, default in [
+        ("TORCHSNAPSHOT_MAX_CHUNK_SIZE_BYTES_OVERRIDE", knobs.get_max_chunk_size_bytes, 512 << 20),
+        ("TORCHSNAPSHOT_MAX_SHARD_SIZE_BYTES_OVERRIDE", knobs.get_max_shard_size_bytes, 512 << 20),
+        ("TORCHSNAPSHOT_SLAB_SIZE_THRESHOLD_BYTES_OVERRIDE", knobs.get_slab_size_threshold_bytes, 128 << 20),
+        ("TORCHSNAPSHOT_MAX_PER_RANK_IO_CONCURRENCY_OVERRIDE", knobs.get_max_per_rank_io_concurrency, 16),
+    ]:
+        monkeypatch.delenv(env, raising=False)
+        assert getter() == default
+        monkeypatch.setenv(env, "12345")
+        assert getter() == 12345
+    monkeypatch.delenv("TORCHSNAPSHOT_DISABLE_BATCHING", raising=False)
+    assert knobs.is_batching_disabled() is False
+    for v in ("1", "true", "True"):
+        monkeypatch.setenv("TORCHSNAPSHOT_DISABLE_BATCHING", v)
+        assert knobs.is_batching_disabled() is True
+    with knobs.override_max_chunk_size_bytes(77):
+        assert knobs.get_max_chunk_size_bytes() == 77
+    monkeypatch.setenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES", "4096")
+    from torchsnapshot_b200.pg_wrapper import PGWrapper
+    from torchsnapshot_b200.scheduler import get_process_memory_budget_bytes
+
+    assert get_process_memory_budget_bytes(PGWrapper(None)) == 4096
