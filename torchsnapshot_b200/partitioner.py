@@ -85,7 +85,9 @@ def _partition_write_loads(
                 give(list(group), path, size)
         else:
             give(list(range(world_size)), path, size)
-    for unit in chunk_units:
+    # sorted: every rank derives the same assignment from the same gathered inputs (set order is hash-seed
+    # dependent and differs between processes)
+    for unit in sorted(chunk_units, key=lambda u: (u.logical_path, u.write_req_idx)):
         r = int(np.argmin(load))
         result[r].append(unit)
         load[r] += unit.size
@@ -104,11 +106,10 @@ def _partition_replicated_write_reqs(
     gathered = [None] * pg.get_world_size()
     pg.all_gather_object(gathered, (entries, loads, non_replicated_size))
     all_entries, all_loads, all_sizes = zip(*gathered)
-    box = [None]
-    if pg.get_rank() == 0:
-        box = [_partition_write_loads(list(all_entries), list(all_loads), list(all_sizes), pg.get_world_size())]
-    pg.broadcast_object_list(box, src=0)
-    mine = sorted((wl.logical_path, wl.write_req_idx) for wl in box[0][pg.get_rank()])
+    # The reference lets rank 0 partition and broadcasts the result (T:partitioner.py:176-192).  The greedy
+    # assignment is a pure function of the gathered inputs, so every rank evaluates it locally: one collective less.
+    result = _partition_write_loads(list(all_entries), list(all_loads), list(all_sizes), pg.get_world_size())
+    mine = sorted((wl.logical_path, wl.write_req_idx) for wl in result[pg.get_rank()])
     new_entries: Dict[str, Entry] = {}
     new_reqs: Dict[str, List[WriteReq]] = defaultdict(list)
     for path, idx in mine:

@@ -39,11 +39,19 @@ _AVAILABLE_MEMORY_MULTIPLIER = 0.6
 _MAX_PER_RANK_CPU_CONCURRENCY = 4
 
 
+_LOCAL_WORLD: Dict[Tuple[int, int], int] = {}
+
+
 def get_local_world_size(pg: PGWrapper) -> int:
-    me = socket.gethostname()
-    names = [None] * pg.get_world_size()
-    pg.all_gather_object(names, me)
-    return sum(1 for n in names if n == me)
+    """Ranks of `pg` on this host (T:scheduler.py:35-44).  Host placement does not change during a job, so the
+    hostname all-gather is paid once per process group instead of once per snapshot."""
+    key = (id(pg.pg), pg.get_world_size())
+    if key not in _LOCAL_WORLD:
+        me = socket.gethostname()
+        names = [None] * pg.get_world_size()
+        pg.all_gather_object(names, me)
+        _LOCAL_WORLD[key] = sum(1 for n in names if n == me)
+    return _LOCAL_WORLD[key]
 
 
 def get_process_memory_budget_bytes(pg: PGWrapper) -> int:

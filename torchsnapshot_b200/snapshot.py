@@ -370,14 +370,15 @@ class Snapshot:
 
     @classmethod
     def _coalesce_path_and_replicated(cls, path: str, pgw: PGWrapper, app_state: AppState, replicated: List[str]) -> Tuple[str, Set[str]]:
-        box = [path]
-        pgw.broadcast_object_list(box, src=0)
-        if box[0] != path:
-            logger.warning(f"Rank {pgw.get_rank()} specified a path ({path}) different from rank 0 ({box[0]}). Using path specified by rank 0.")
+        # one exchange carries the path (rank 0's wins, T:snapshot.py:871-877) and the replication globs
+        # (T:snapshot.py:880-887); the reference spends a broadcast and an all-gather on them
         globs = cls._infer_replicated(replicated, app_state)
         everyone: List[Any] = [None] * pgw.get_world_size()
-        pgw.all_gather_object(everyone, globs)
-        return box[0], cls._coalesce_replicated(everyone)
+        pgw.all_gather_object(everyone, (path, globs))
+        chosen = everyone[0][0]
+        if chosen != path:
+            logger.warning(f"Rank {pgw.get_rank()} specified a path ({path}) different from rank 0 ({chosen}). Using path specified by rank 0.")
+        return chosen, cls._coalesce_replicated([g for _, g in everyone])
 
     @staticmethod
     def _coalesce_replicated(global_replicated: List[List[str]]) -> Set[str]:
@@ -406,16 +407,13 @@ class Snapshot:
         mine = [p for p, v in flattened.items() if not is_sharded(v) and any(fnmatch.fnmatch(p, g) for g in replicated)]
         everyone: List[Any] = [None] * pgw.get_world_size()
         pgw.all_gather_object(everyone, mine)
-        box: List[Any] = [[]]
-        if pgw.get_rank() == 0:
-            # replicated only if present on every rank (T:snapshot.py:656-666)
-            count: Dict[str, int] = defaultdict(int)
-            for paths in everyone:
-                for p in paths:
-                    count[p] += 1
-            box = [[p for p in mine if count[p] == pgw.get_world_size()]]
-        pgw.broadcast_object_list(box, src=0)
-        return set(box[0])
+        # replicated only if present on every rank (T:snapshot.py:656-666).  The reference computes this on rank 0 and
+        # broadcasts it; the answer is a function of the gathered lists, so each rank derives it locally.
+        count: Dict[str, int] = defaultdict(int)
+        for paths in everyone:
+            for p in set(paths):
+                count[p] += 1
+        return {p for p, c in count.items() if c == pgw.get_world_size()}
 
     @staticmethod
     def _gather_manifest(manifest: Dict[str, Entry], pgw: PGWrapper) -> Dict[str, Entry]:
