@@ -466,7 +466,8 @@ def run_ours(args, rank: int, world: int, device: torch.device, base_dir: str) -
         "engine_step": {k: last_stats.get(k) for k in ("plan_ms", "kernel_ms", "copy_ms", "device_done_ms", "total_ms", "n_files", "n_members", "n_tiles_bulk", "n_tiles_lsu", "n_kernel_launches")},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "host": {"cpu_count": os.cpu_count()},
+        "host": {"cpu_count": os.cpu_count(), "ranks_on_host": world, "cores_per_rank": (os.cpu_count() or 0) // max(1, world),
+                 "engine_io_threads_per_rank": int(os.environ.get("TSNAP_B200_IO_THREADS", max(2, 16 // max(1, world))))},
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
