@@ -29,9 +29,17 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.h"
 
 namespace tsnap {
+
+// NVTX ranges make the pack / drain / write overlap visible in a timeline profiler (no-ops when none is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_err;
 int set_err(int code, const std::string& msg) {
@@ -608,6 +616,7 @@ static void account_parts(tsnap_job* job, int64_t async_parts) {
 }
 
 static int run_save_inner(tsnap_job* job) {
+    NvtxRange nvtx_job("tsnap:save_job issue (plan, pack launch, D2H issue)");
     tsnap_engine* eng = job->eng;
     int rc = ensure_ring(eng);
     if (rc != TSNAP_OK) return rc;
@@ -724,6 +733,7 @@ static int run_save_inner(tsnap_job* job) {
                     auto tq = clk::now();
                     eng->io->post([eng, job, fp, slot, lo, n, tq] {
                         job->io_queue_us += int64_t(ms_since(tq) * 1000.0);
+                        NvtxRange nvtx_w("tsnap:pwrite chunk");
                         auto tb = clk::now();
                         static const bool dbg_skip_write = getenv("TSNAP_B200_DEBUG_SKIP_WRITE") != nullptr;  // experiments only
                         if (!dbg_skip_write && !job->failed() && pwrite_all(fp->fd, slot, n, lo) != 0)
@@ -762,6 +772,7 @@ struct LoadShared {
 };
 
 static int run_load_inner(tsnap_job* job) {
+    NvtxRange nvtx_job("tsnap:load_job issue (plan, reads)");
     tsnap_engine* eng = job->eng;
     int rc = ensure_ring(eng);
     if (rc != TSNAP_OK) return rc;
@@ -821,6 +832,7 @@ static int run_load_inner(tsnap_job* job) {
                 const uint64_t n = std::min(sb, f->nbytes - lo);
                 char* slot = eng->ring.acquire();
                 eng->io->post([eng, job, w, wi, f, base, slot, lo, n, shared, last_wave] {
+                    NvtxRange nvtx_r("tsnap:pread chunk + H2D enqueue");
                     cudaSetDevice(eng->device);
                     bool ok = !job->failed();
                     if (ok && f->mem_src) {
