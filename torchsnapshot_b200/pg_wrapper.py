@@ -18,19 +18,23 @@ class PGWrapper:
     def get_world_size(self) -> int:
         return 1 if self.pg is None else dist.get_world_size(group=self.pg)
 
+    def _alone(self) -> bool:
+        # a one-rank group needs no communication: object collectives would still pickle and copy (≈0.3–2 ms each)
+        return self.pg is None or self.get_world_size() == 1
+
     def barrier(self) -> None:
-        if self.pg is not None:
+        if not self._alone():
             if dist.get_backend(self.pg) == "nccl":
                 dist.barrier(group=self.pg, device_ids=[torch.cuda.current_device()])
             else:
                 dist.barrier(group=self.pg)
 
     def broadcast_object_list(self, obj_list: List[Any], src: int = 0) -> None:
-        if self.pg is not None:
+        if not self._alone():
             dist.broadcast_object_list(obj_list, src=dist.get_global_rank(self.pg, src), group=self.pg)
 
     def all_gather_object(self, obj_list: List[Any], obj: Any) -> None:
-        if self.pg is None:
+        if self._alone():
             obj_list[0] = obj
         else:
             dist.all_gather_object(obj_list, obj, group=self.pg)
@@ -47,7 +51,7 @@ class PGWrapper:
                     f"The length of input_list {len(input_list)} for scatter_object_list "
                     f"must be the same as the process group's world size ({world})."
                 )
-        if self.pg is None:
+        if self._alone():
             output_list[0] = input_list[0]  # type: ignore[index]
             return
         if dist.get_backend(self.pg) == "nccl":
