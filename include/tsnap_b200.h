@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TSNAP_ABI_VERSION 1
+#define TSNAP_ABI_VERSION 2
 #define TSNAP_MAX_DIMS 8
 
 /* error codes */
@@ -106,6 +106,15 @@ typedef struct tsnap_engine_config {
 
 #define TSNAP_ENGINE_NO_BULK 1u   /* force the LSU kernel for every tile (A/B for the ncu captures) */
 #define TSNAP_ENGINE_FSYNC 2u     /* fsync each file before the job reports completion ("durable") */
+#define TSNAP_ENGINE_ODIRECT 4u   /* open payload files O_DIRECT: the pinned ring is DMA'd to/from the block device
+                                     without a page-cache copy (4 KiB-aligned chunk I/O, ragged tails are written
+                                     padded and cut with ftruncate).  Falls back to buffered I/O per file when the
+                                     filesystem refuses O_DIRECT (tmpfs).  Replaces aiofiles.open+write / read of
+                                     FSStoragePlugin (T:storage_plugins/fs.py:28-51). */
+#define TSNAP_ENGINE_TRACE 8u     /* record a per-chunk timeline (tsnap_job_get_trace) */
+#define TSNAP_ENGINE_NO_ARENA 16u /* never stage in HBM: dense members are drained straight from the live tensors
+                                     (what the engine also does by itself when HBM is too full for an arena — the
+                                     reference's OOM fallback to a CPU slab, T:batcher.py:144-152) */
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int tsnap_abi_version(void);
@@ -171,8 +180,60 @@ typedef struct tsnap_job_stats {
     double io_queue_ms;         /* sum over chunks of (write start - D2H complete): I/O queueing delay */
     double copy_ms;             /* CUDA-event span of the payload D2H copies on the copy stream
                                    (first copy start -> last copy end); 0 for load jobs      */
+    uint64_t arena_bytes;       /* HBM staging used by the job (0 = arena-less)              */
+    uint64_t n_waves;           /* arena waves                                               */
+    uint64_t direct_bytes;      /* payload drained straight from the live tensors (no pack)  */
+    uint64_t n_memcpy;          /* cudaMemcpyAsync calls issued for payload                  */
 } tsnap_job_stats;
 int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
+
+/* ---- HBM staging arena supplied by the caller ---------------------------------------------------
+ * By default the engine owns a cudaMalloc'ed arena.  A host runtime with its own device allocator
+ * (PyTorch's caching allocator) lends one per job instead, so the staging bytes stay visible to — and
+ * reusable by — that allocator: the GPU slab of GPUBatchedBufferStager is a torch.cuda.ByteTensor too
+ * (T:batcher.py:147).  tsnap_job_arena_hint reports what the job could use; tsnap_job_set_arena must
+ * be called before submit, the memory must stay valid until the job is done.  bytes == 0 selects the
+ * arena-less mode for this job (see TSNAP_ENGINE_NO_ARENA). */
+typedef struct tsnap_arena_hint {
+    uint64_t total_bytes;          /* every device file at a 256 B-aligned offset: one-wave size   */
+    uint64_t largest_file_bytes;   /* two-wave operation needs 2 x this                            */
+    uint64_t strided_total_bytes;  /* files with a strided / converting member: these cannot be    */
+    uint64_t strided_largest_bytes;/*   drained without staging                                    */
+} tsnap_arena_hint;
+int tsnap_job_arena_hint(tsnap_job* job, tsnap_arena_hint* out);
+int tsnap_job_set_arena(tsnap_job* job, void* device_ptr, uint64_t nbytes);
+
+/* ---- timeline of a finished job (engines created with TSNAP_ENGINE_TRACE) ------------------------
+ * One record per pipeline event; times are milliseconds since submit on the host's monotonic clock.
+ * This is the overlap evidence (pack || D2H || pwrite) without an external timeline profiler. */
+enum tsnap_trace_kind {
+    TSNAP_TR_PLAN = 0,      /* host planning + table build                                  */
+    TSNAP_TR_KERNEL = 1,    /* pack / scatter kernels of one wave (duration from CUDA events) */
+    TSNAP_TR_D2H = 2,       /* one chunk: copy-engine busy interval (completion-ordered)      */
+    TSNAP_TR_PWRITE = 3,    /* one chunk: inside pwrite                                      */
+    TSNAP_TR_SLOT_WAIT = 4, /* drain thread blocked on a free pinned slot                     */
+    TSNAP_TR_PREAD = 5,     /* one chunk: inside pread                                       */
+    TSNAP_TR_H2D = 6,       /* one chunk: upload, completion-ordered                          */
+    TSNAP_TR_OPEN = 7       /* file create/open                                              */
+};
+typedef struct tsnap_trace_rec {
+    int32_t kind;   /* enum tsnap_trace_kind */
+    int32_t lane;   /* worker thread ordinal (I/O records), wave (kernel records), else 0 */
+    int32_t file;   /* file index or -1 */
+    int32_t reserved;
+    double t0_ms, t1_ms;
+    uint64_t bytes;
+} tsnap_trace_rec;
+/* copies up to `cap` records into `out`; *n receives the total number available */
+int tsnap_job_get_trace(tsnap_job* job, tsnap_trace_rec* out, uint64_t cap, uint64_t* n);
+
+/* ---- roofline probes: the engine's own link and sink, measured with its own ring and workers -----
+ * D2H/H2D: `bytes` moved in ring-slot-sized cudaMemcpyAsync chunks between a scratch HBM buffer and
+ * the pinned ring.  WRITE: `bytes` written from the ring to fresh files under `dir` by the I/O workers
+ * (same chunking/interleaving as a save job, no D2H); READ reads those files back into the ring.
+ * The caller removes `dir`.  out_gbs: bytes / 1e9 / seconds. */
+enum tsnap_probe_kind { TSNAP_PROBE_D2H = 0, TSNAP_PROBE_H2D = 1, TSNAP_PROBE_WRITE = 2, TSNAP_PROBE_READ = 3 };
+int tsnap_engine_probe(tsnap_engine* eng, int kind, const char* dir, uint64_t bytes, double* out_gbs);
 
 /* ---- load job: pread -> pinned ring -> H2D -> unpack/scatter kernel ---------------------------
  * add_file == one (batched) ReadReq: path + byte range (T:io_types.py:52-56, merged per file like
@@ -181,8 +242,11 @@ int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
 int tsnap_load_job_create(tsnap_engine* eng, tsnap_job** out);
 int tsnap_load_job_add_file(tsnap_job* job, const char* path, uint64_t offset, uint64_t nbytes, int32_t* file_index);
 int tsnap_load_job_add_member(tsnap_job* job, int32_t file_index, const tsnap_copy_desc* desc);
-/* the scatter kernels run on the engine's stream; `consumer_stream` (may be NULL) is made to wait
- * for them before tsnap_job_wait returns. */
+/* The scatter kernels run on the engine's stream, ORDERED AFTER everything already enqueued on
+ * `consumer_stream` (a cudaStream_t passed as void*; NULL = legacy default stream) at submit time — work
+ * that still writes the destination tensors (init kernels, an in-flight optimizer step) cannot land after
+ * the restored bytes, like the reference's dst.copy_() on the current stream (T:io_preparers/tensor.py:358-360).
+ * tsnap_job_wait returns after the scatter kernels have finished, so later work on any stream sees them. */
 int tsnap_load_job_submit(tsnap_job* job, void* consumer_stream);
 
 /* ---- stager/consumer seam for arbitrary StoragePlugins -----------------------------------------

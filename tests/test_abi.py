@@ -19,7 +19,7 @@ def test_every_declared_symbol_is_exported():
 
 
 def test_abi_version_and_dtype_sizes():
-    assert _native.lib.tsnap_abi_version() == 1
+    assert _native.lib.tsnap_abi_version() == 2
     import torch
 
     for dt, code in _native.TORCH_TO_TSNAP.items():
@@ -30,6 +30,9 @@ def test_struct_layouts_match_header():
     # sizes the C side assumes (checked indirectly: a wrong layout breaks every parity test, this localises it)
     assert ctypes.sizeof(_native.CopyDesc) == 8 + 8 + 3 * 8 * 8 + 6 * 4
     assert ctypes.sizeof(_native.EngineConfig) == 32
+    assert ctypes.sizeof(_native.TraceRec) == 40
+    assert ctypes.sizeof(_native.ArenaHint) == 32
+    assert ctypes.sizeof(_native.JobStats) == 21 * 8
 
 
 def test_device_engine_fails_loudly_without_gpu():

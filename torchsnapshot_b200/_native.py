@@ -25,6 +25,12 @@ SPACE_DEVICE, SPACE_HOST, SPACE_WIRE = 0, 1, 2
 
 ENGINE_NO_BULK = 1
 ENGINE_FSYNC = 2
+ENGINE_ODIRECT = 4
+ENGINE_TRACE = 8
+ENGINE_NO_ARENA = 16
+
+PROBE_D2H, PROBE_H2D, PROBE_WRITE, PROBE_READ = 0, 1, 2, 3
+TRACE_KINDS = ("plan", "kernel", "d2h", "pwrite", "slot_wait", "pread", "h2d", "open")
 
 # the ten buffer-protocol dtypes of the reference (T:serialization.py:162-173)
 TORCH_TO_TSNAP = {
@@ -107,10 +113,35 @@ class JobStats(C.Structure):
         ("io_busy_ms", C.c_double),
         ("io_queue_ms", C.c_double),
         ("copy_ms", C.c_double),
+        ("arena_bytes", C.c_uint64),
+        ("n_waves", C.c_uint64),
+        ("direct_bytes", C.c_uint64),
+        ("n_memcpy", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ArenaHint(C.Structure):
+    _fields_ = [
+        ("total_bytes", C.c_uint64),
+        ("largest_file_bytes", C.c_uint64),
+        ("strided_total_bytes", C.c_uint64),
+        ("strided_largest_bytes", C.c_uint64),
+    ]
+
+
+class TraceRec(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("lane", C.c_int32),
+        ("file", C.c_int32),
+        ("reserved", C.c_int32),
+        ("t0_ms", C.c_double),
+        ("t1_ms", C.c_double),
+        ("bytes", C.c_uint64),
+    ]
 
 
 class PlanInfo(C.Structure):
@@ -156,6 +187,10 @@ EXPORTED_SYMBOLS = [
     "tsnap_consume",
     "tsnap_plan_describe",
     "tsnap_host_execute",
+    "tsnap_job_arena_hint",
+    "tsnap_job_set_arena",
+    "tsnap_job_get_trace",
+    "tsnap_engine_probe",
 ]
 
 
@@ -196,11 +231,15 @@ def _load() -> C.CDLL:
     lib.tsnap_consume.argtypes = [vp, vp, C.c_uint64, C.POINTER(CopyDesc), C.c_int32, vp]
     lib.tsnap_plan_describe.argtypes = [C.POINTER(CopyDesc), C.c_int32, C.c_uint64, C.POINTER(PlanInfo)]
     lib.tsnap_host_execute.argtypes = [C.POINTER(CopyDesc), C.c_int32, vp, C.c_uint64, C.c_int32]
+    lib.tsnap_job_arena_hint.argtypes = [vp, C.POINTER(ArenaHint)]
+    lib.tsnap_job_set_arena.argtypes = [vp, vp, C.c_uint64]
+    lib.tsnap_job_get_trace.argtypes = [vp, C.POINTER(TraceRec), C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.tsnap_engine_probe.argtypes = [vp, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_double)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tsnap_last_error", "tsnap_dtype_size"):
             fn.restype = C.c_int
-    if lib.tsnap_abi_version() != 1:
+    if lib.tsnap_abi_version() != 2:
         raise ImportError("libtsnap_b200.so ABI version mismatch; rebuild it")
     return lib
 
@@ -296,6 +335,7 @@ class Job:
         self._h = handle
         self._save = save
         self._keepalive: List[object] = []
+        self._arena: Optional[torch.Tensor] = None
         self._destroyed = False
 
     def add_file(self, path: str, nbytes: int, offset: int = 0) -> int:
@@ -312,9 +352,79 @@ class Job:
         if keepalive is not None:
             self._keepalive.append(keepalive)
 
+    def arena_hint(self) -> dict:
+        h = ArenaHint()
+        check(lib.tsnap_job_arena_hint(self._h, C.byref(h)))
+        return {k: getattr(h, k) for k, _ in h._fields_}
+
+    def set_arena(self, tensor: Optional[torch.Tensor]) -> None:
+        """Lend the job its HBM staging (a uint8 CUDA tensor, kept alive until the job is destroyed); None selects the
+        arena-less mode: dense members are drained straight from the live tensors."""
+        if tensor is None:
+            check(lib.tsnap_job_set_arena(self._h, None, 0))
+            return
+        check(lib.tsnap_job_set_arena(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size()))
+        self._arena = tensor
+
+    def _provision_arena(self) -> None:
+        """HBM staging comes from PyTorch's caching allocator, so it is visible to — and reusable by — the training job
+        the moment the snapshot has drained (the reference's GPU slab is a torch.cuda.ByteTensor too, T:batcher.py:147).
+        Policy: the whole payload when that leaves max(1/8 of HBM, 4 GiB) free; else as much as that reserve allows if it
+        still holds two of the largest files (multi-wave staging); else no arena — dense members then go over the link
+        straight from the live tensors and only strided/converting members are staged (the reference falls back to a
+        CPU slab when its GPU slab OOMs, T:batcher.py:148-152)."""
+        dev = self.engine.device
+        if dev < 0 or self.engine.owns_arena:
+            return
+        hint = self.arena_hint()
+        total, largest = hint["total_bytes"], hint["largest_file_bytes"]
+        if total == 0:
+            return
+        if self.engine.flags & ENGINE_NO_ARENA:
+            self.set_arena(None)
+            return
+        cap = self.engine.hbm_staging_bytes
+        with torch.cuda.device(dev):
+            free_b, total_b = torch.cuda.mem_get_info(dev)
+            cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            reserve = max(total_b // 8, 4 << 30)
+            allowed = max(0, free_b + cached - reserve)
+            if cap:
+                allowed = min(allowed, cap)
+            cands = []
+            if total <= allowed:
+                cands.append(total)
+            elif allowed >= 2 * largest:
+                cands.append(allowed)
+            nd_total, nd_largest = hint["strided_total_bytes"], hint["strided_largest_bytes"]
+            if nd_total:
+                if nd_total <= allowed and nd_total not in cands:
+                    cands.append(nd_total)
+                cands.append(min(nd_total, 2 * nd_largest))
+            for i, want in enumerate(cands):
+                want = (want + (2 << 20) - 1) // (2 << 20) * (2 << 20)
+                for attempt in range(2):
+                    try:
+                        self.set_arena(torch.empty(want, dtype=torch.uint8, device=f"cuda:{dev}"))
+                        return
+                    except torch.OutOfMemoryError:
+                        if attempt == 0:
+                            torch.cuda.empty_cache()  # give cached-but-fragmented blocks back and retry once
+            self.set_arena(None)
+
     def submit(self, stream: Optional[int] = None) -> None:
+        self._provision_arena()
         fn = lib.tsnap_save_job_submit if self._save else lib.tsnap_load_job_submit
         check(fn(self._h, C.c_void_p(stream or 0)))
+
+    def trace(self) -> List[dict]:
+        n = C.c_uint64(0)
+        check(lib.tsnap_job_get_trace(self._h, None, 0, C.byref(n)))
+        if n.value == 0:
+            return []
+        arr = (TraceRec * n.value)()
+        check(lib.tsnap_job_get_trace(self._h, arr, n.value, C.byref(n)))
+        return [dict(kind=TRACE_KINDS[r.kind], lane=r.lane, file=r.file, t0_ms=r.t0_ms, t1_ms=r.t1_ms, bytes=r.bytes) for r in arr]
 
     def wait_device(self) -> None:
         check(lib.tsnap_job_wait_device(self._h))
@@ -333,8 +443,9 @@ class Job:
     def destroy(self) -> None:
         if not self._destroyed:
             self._destroyed = True
-            lib.tsnap_job_destroy(self._h)
+            lib.tsnap_job_destroy(self._h)  # waits for the job: nothing reads the arena any more
             self._keepalive.clear()
+            self._arena = None
 
     def __del__(self) -> None:  # pragma: no cover - best effort
         try:
@@ -400,6 +511,11 @@ class Engine:
         check(lib.tsnap_engine_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.device = device
+        self.flags = flags
+        self.hbm_staging_bytes = hbm_staging_bytes
+        # TSNAP_B200_ENGINE_ARENA=1: staging is the engine's own cudaMalloc'ed arena (what a C caller gets) instead
+        # of memory lent from PyTorch's allocator
+        self.owns_arena = os.environ.get("TSNAP_B200_ENGINE_ARENA", "0") == "1"
         self._closed = False
 
     def save_job(self) -> Job:
@@ -418,7 +534,13 @@ class Engine:
         check(lib.tsnap_stage_submit(self._h, arr, len(descs), nbytes, C.c_void_p(stream or 0), C.byref(h)))
         return StagedBuffer(self, h, nbytes, list(keepalive or []))
 
-    def consume(self, buf, descs: Sequence[CopyDesc]) -> None:
+    def probe(self, kind: int, nbytes: int, directory: Optional[str] = None) -> float:
+        """GB/s of the engine's own link (PROBE_D2H/H2D) or sink/source (PROBE_WRITE/READ under `directory`)."""
+        out = C.c_double(0.0)
+        check(lib.tsnap_engine_probe(self._h, kind, os.fsencode(directory) if directory else None, nbytes, C.byref(out)))
+        return out.value
+
+    def consume(self, buf, descs: Sequence[CopyDesc], stream: Optional[int] = None) -> None:
         mv = memoryview(buf).cast("B")
         n = mv.nbytes
         if n == 0:
@@ -431,7 +553,9 @@ class Engine:
         else:
             addr = C.addressof(C.c_char.from_buffer(mv))
         arr = _desc_array(descs)
-        check(lib.tsnap_consume(self._h, C.c_void_p(addr), n, arr, len(descs), None))
+        if stream is None and self.device >= 0:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib.tsnap_consume(self._h, C.c_void_p(addr), n, arr, len(descs), C.c_void_p(stream or 0)))
 
     def stats(self) -> dict:
         st = EngineStats()

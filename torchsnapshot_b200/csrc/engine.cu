@@ -22,6 +22,8 @@
 #include <sched.h>
 #include <fcntl.h>
 #include <string.h>
+#include <dirent.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -125,13 +127,55 @@ static std::vector<int> gpu_numa_cpus(int device) {
     return cpus;
 }
 
+// Placement of the I/O workers (TSNAP_B200_IO_PIN):
+//   none   (default) leave it to the scheduler
+//   local  all workers on the CPUs of the GPU's NUMA node
+//   spread one physical core per worker, alternating between the NUMA nodes (page-cache copies are bound by
+//          per-node locks and memory channels: both sockets' worth helps), offset by LOCAL_RANK so that ranks
+//          sharing a host do not pile onto the same cores
+static std::vector<std::vector<int>> io_worker_cpus(int n, const std::vector<int>& gpu_node_cpus) {
+    const char* env = getenv("TSNAP_B200_IO_PIN");
+    std::string mode = env ? env : "none";
+    if (mode == "local") return {gpu_node_cpus};
+    if (mode != "spread") return {};
+    cpu_set_t cur;
+    const bool have_aff = sched_getaffinity(0, sizeof(cur), &cur) == 0;
+    std::vector<std::vector<int>> node_cores;  // per node: first hardware thread of every allowed physical core
+    for (int node = 0; node < 16; ++node) {
+        std::string cl = read_small_file("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+        if (cl.empty()) break;
+        std::vector<int> cores;
+        for (int c : parse_cpulist(cl)) {
+            if (have_aff && (c >= CPU_SETSIZE || !CPU_ISSET(c, &cur))) continue;
+            std::vector<int> sib = parse_cpulist(read_small_file("/sys/devices/system/cpu/cpu" + std::to_string(c) + "/topology/thread_siblings_list"));
+            if (!sib.empty() && sib[0] != c) continue;
+            cores.push_back(c);
+        }
+        if (!cores.empty()) node_cores.push_back(cores);
+    }
+    if (node_cores.empty()) return {};
+    const char* lr = getenv("LOCAL_RANK");
+    const int rank = lr ? atoi(lr) : 0;
+    std::vector<std::vector<int>> out;
+    for (int i = 0; i < n; ++i) {
+        const int g = rank * n + i;  // global worker ordinal on this host
+        const std::vector<int>& cores = node_cores[size_t(g) % node_cores.size()];
+        out.push_back({cores[(size_t(g) / node_cores.size()) % cores.size()]});
+    }
+    return out;
+}
+
 // ---- WorkerPool ---------------------------------------------------------------------------------------
-WorkerPool::WorkerPool(int n, const std::vector<int>& cpus) {
-    for (int i = 0; i < n; ++i)
-        threads_.emplace_back([this, cpus] {
-            bind_current_thread(cpus);
+static thread_local int g_lane = 0;  // ordinal of the current I/O worker (trace lanes)
+WorkerPool::WorkerPool(int n, const std::vector<std::vector<int>>& cpus) {
+    for (int i = 0; i < n; ++i) {
+        std::vector<int> mine = cpus.empty() ? std::vector<int>() : cpus[size_t(i) % cpus.size()];
+        threads_.emplace_back([this, mine, i] {
+            g_lane = i;
+            bind_current_thread(mine);
             run();
         });
+    }
 }
 WorkerPool::~WorkerPool() {
     {
@@ -163,16 +207,18 @@ void WorkerPool::run() {
 }
 
 // ---- SlotRing -------------------------------------------------------------------------------------------
-int SlotRing::init(size_t slot_bytes, int n, bool pinned) {
+int SlotRing::init(size_t slot_bytes, int n, bool pinned, size_t slack) {
     slot_bytes_ = slot_bytes;
+    slack_ = slack;
     pinned_ = pinned;
     for (int i = 0; i < n; ++i) {
         void* p = nullptr;
         if (pinned) {
-            cudaError_t e = cudaHostAlloc(&p, slot_bytes, cudaHostAllocDefault);
+            // cudaHostAlloc returns page-aligned memory: fit for O_DIRECT as it is
+            cudaError_t e = cudaHostAlloc(&p, slot_bytes + slack, cudaHostAllocDefault);
             if (e != cudaSuccess) return set_err(TSNAP_ECUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
         } else {
-            if (posix_memalign(&p, 4096, slot_bytes) != 0) return set_err(TSNAP_ENOMEM, "posix_memalign failed");
+            if (posix_memalign(&p, 4096, slot_bytes + slack) != 0) return set_err(TSNAP_ENOMEM, "posix_memalign failed");
         }
         all_.push_back(static_cast<char*>(p));
         free_.push_back(static_cast<char*>(p));
@@ -262,6 +308,10 @@ void tsnap_job::fail(int code, const std::string& msg) {
         err_msg = msg;
     }
 }
+void tsnap_job::add_trace(int kind, int lane, int file, double t0, double t1, uint64_t bytes) {
+    std::lock_guard<std::mutex> g(trace_mu);
+    trace.push_back(tsnap_trace_rec{kind, lane, file, 0, t0, t1, bytes});
+}
 bool tsnap_job::failed() {
     std::lock_guard<std::mutex> g(mu);
     return err_code != 0;
@@ -332,11 +382,12 @@ static void completion_main(tsnap_engine* eng) {
 
 // ---- planning of one wave ----------------------------------------------------------------------------------
 static int plan_wave(tsnap_job* job, Wave& w) {
+    if (w.direct) return TSNAP_OK;
     tsnap_engine* eng = job->eng;
     std::string err;
     for (int fi : w.files) {
         FileSpec& f = job->files[fi];
-        const uint64_t wire_base = uint64_t(uintptr_t(eng->arena)) + w.region_off + f.arena_off;
+        const uint64_t wire_base = uint64_t(uintptr_t(job->arena)) + w.region_off + f.arena_off;
         for (const tsnap_copy_desc& d : f.members) {
             NormalizedCopy nc;
             int rc = normalize_copy(d, wire_base, eng->allow_bulk, &nc, &err);
@@ -400,84 +451,149 @@ static int launch_wave(tsnap_job* job, Wave& w) {
 
 static void collect_wave_timing(tsnap_job* job, Wave& w) {
     float a = 0, b = 0;
-    if (w.ev_k0 && cudaEventElapsedTime(&a, w.ev_k0, w.ev_k1) == cudaSuccess &&
-        cudaEventElapsedTime(&b, w.ev_k1, w.ev_k2) == cudaSuccess) {
+    if (w.timed || !w.ev_k0) return;
+    if (cudaEventElapsedTime(&a, w.ev_k0, w.ev_k1) == cudaSuccess && cudaEventElapsedTime(&b, w.ev_k1, w.ev_k2) == cudaSuccess) {
         std::lock_guard<std::mutex> g(job->mu);
+        w.timed = true;
         job->stats.kernel_bulk_ms += a;
         job->stats.kernel_lsu_ms += b;
         job->stats.kernel_ms += a + b;
+        w.kernel_ms = a + b;
     }
 }
 
-static int ensure_arena(tsnap_engine* eng, uint64_t need, uint64_t largest_file) {
-    if (need <= eng->arena_bytes) return TSNAP_OK;
+// What a job asks of the HBM staging arena.
+struct ArenaNeed {
+    uint64_t total = 0, largest = 0;          // all device files
+    uint64_t nd_total = 0, nd_largest = 0;    // files that cannot be drained without staging (strided / cast members)
+};
+static ArenaNeed arena_need(const tsnap_job* job) {
+    ArenaNeed n;
+    for (const FileSpec& f : job->files) {
+        if (f.host_only || f.nbytes == 0) continue;
+        const uint64_t fb = align_up(f.nbytes, 256);
+        n.total += fb;
+        n.largest = std::max(n.largest, fb);
+        if (!f.dense) {
+            n.nd_total += fb;
+            n.nd_largest = std::max(n.nd_largest, fb);
+        }
+    }
+    return n;
+}
+
+// Engine-owned arena (callers that lend none): grow towards the best operating point that fits — the whole
+// payload, else two half-arenas of the largest file, else just the strided files — and never fail: with no arena
+// at all the job drains dense members straight from the live tensors (the reference's fallback when its GPU slab
+// allocation OOMs is a CPU slab, T:batcher.py:144-152).
+static void ensure_arena(tsnap_engine* eng, const ArenaNeed& need) {
+    if (need.total <= eng->arena_bytes) return;
     size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
     const uint64_t reserve = std::max<uint64_t>(total_b / 8, 4ull << 30);
     uint64_t allowed = eng->arena_bytes + (free_b > reserve ? free_b - reserve : 0);
     if (eng->cfg.hbm_staging_bytes) allowed = std::min<uint64_t>(allowed, eng->cfg.hbm_staging_bytes);
-    uint64_t target = std::min(need, allowed);
-    if (target < need) {
-        // multi-wave mode needs two half-arenas that each hold the largest file
-        const uint64_t min_two = 2 * align_up(largest_file, 256);
-        if (target < min_two) target = min_two;
-        if (target > eng->arena_bytes + free_b)
-            return set_err(TSNAP_ECUDA, "not enough free HBM for the staging arena");
+    // candidate sizes, best first: the whole payload; as much as the reserve policy allows when that still holds two
+    // largest files (multi-wave); else only what the strided files need — that much is taken even below the reserve
+    // line, because those members cannot be drained without staging
+    uint64_t cands[4] = {0, 0, 0, 0};
+    if (need.total <= allowed) cands[0] = need.total;
+    else if (allowed >= 2 * need.largest) cands[1] = allowed;
+    if (need.nd_total && need.nd_total <= allowed) cands[2] = need.nd_total;
+    cands[3] = std::min(need.nd_total, 2 * need.nd_largest);
+    for (int i = 0; i < 4; ++i) {
+        if (cands[i] == 0) continue;
+        const uint64_t target = align_up(cands[i], 2ull << 20);
+        if (target <= eng->arena_bytes) return;  // what we hold is already as good as this candidate
+        if (target > eng->arena_bytes + free_b) continue;
+        if (eng->arena) {
+            cudaStreamSynchronize(eng->s_kernel);
+            cudaStreamSynchronize(eng->s_copy);
+            cudaFree(eng->arena);
+            eng->arena = nullptr;
+            eng->arena_bytes = 0;
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, target) == cudaSuccess) {
+            eng->arena = static_cast<char*>(p);
+            eng->arena_bytes = target;
+            return;
+        }
+        cudaGetLastError();  // clear the OOM and look again at what is free
+        cudaMemGetInfo(&free_b, &total_b);
     }
-    target = align_up(target, 2ull << 20);
-    if (target <= eng->arena_bytes) return TSNAP_OK;
-    if (eng->arena) {
-        CUDA_TRY(cudaStreamSynchronize(eng->s_kernel));
-        CUDA_TRY(cudaStreamSynchronize(eng->s_copy));
-        CUDA_TRY(cudaFree(eng->arena));
-        eng->arena = nullptr;
-        eng->arena_bytes = 0;
-    }
-    void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, target));
-    eng->arena = static_cast<char*>(p);
-    eng->arena_bytes = target;
-    return TSNAP_OK;
 }
 
 static int ensure_ring(tsnap_engine* eng) {
-    if (eng->ring.total_bytes() > 0) return TSNAP_OK;
-    const size_t sb = eng->cfg.pinned_slot_bytes ? eng->cfg.pinned_slot_bytes : (32ull << 20);
+    if (eng->ring.count() > 0) return TSNAP_OK;
+    size_t sb = eng->cfg.pinned_slot_bytes ? eng->cfg.pinned_slot_bytes : (32ull << 20);
+    sb = align_up(sb, 4096);
     const int n = eng->cfg.pinned_slots ? eng->cfg.pinned_slots : 32;
-    return eng->ring.init(sb, n, eng->has_device);
+    return eng->ring.init(sb, n, eng->has_device, 8192);
 }
 
-// groups the device files of a job into waves that fit the arena
+// Decides, per device file, between staging in the arena (pack/scatter kernels) and the direct link path, and
+// groups the staged files into waves that fit the arena.  job->waves = staged waves, then at most one direct wave.
 static int build_waves(tsnap_job* job) {
     tsnap_engine* eng = job->eng;
-    uint64_t total = 0, largest = 0;
-    std::vector<int> dev_files;
+    const ArenaNeed need = arena_need(job);
+    if (need.total == 0) return TSNAP_OK;
+    if (!eng->has_device) return set_err(TSNAP_ECUDA, "job has device members but the engine is host-only");
+    if (eng->no_arena) {
+        job->arena = nullptr;
+        job->arena_bytes = 0;
+    } else if (!job->arena_set) {
+        ensure_arena(eng, need);
+        job->arena = eng->arena;
+        job->arena_bytes = eng->arena_bytes;
+    }
+    const uint64_t A = job->arena_bytes;
+    bool stage_dense;
+    uint64_t staged_total, staged_largest;
+    if (A >= need.total || (A >= 2 * need.largest && need.largest > 0)) {
+        stage_dense = true;
+        staged_total = need.total;
+        staged_largest = need.largest;
+    } else {
+        stage_dense = false;
+        staged_total = need.nd_total;
+        staged_largest = need.nd_largest;
+        if (staged_total > A && 2 * staged_largest > A)
+            return set_err(TSNAP_ECUDA, "not enough HBM staging for the strided/converting members: have " + std::to_string(A) +
+                                            " bytes, need " + std::to_string(std::min(staged_total, 2 * staged_largest)));
+    }
+    const bool single = staged_total <= A;
+    const uint64_t cap = single ? A : (A / 2) / 256 * 256;
+    std::vector<int> direct_files;
     for (size_t i = 0; i < job->files.size(); ++i) {
         FileSpec& f = job->files[i];
         if (f.host_only || f.nbytes == 0) continue;
-        dev_files.push_back(int(i));
-        total += align_up(f.nbytes, 256);
-        largest = std::max(largest, f.nbytes);
-    }
-    if (dev_files.empty()) return TSNAP_OK;
-    if (!eng->has_device) return set_err(TSNAP_ECUDA, "job has device members but the engine is host-only");
-    int rc = ensure_arena(eng, total, largest);
-    if (rc != TSNAP_OK) return rc;
-    const bool single = total <= eng->arena_bytes;
-    const uint64_t cap = single ? eng->arena_bytes : (eng->arena_bytes / 2) / 256 * 256;
-    job->waves.emplace_back();
-    for (int fi : dev_files) {
-        FileSpec& f = job->files[fi];
+        if (f.dense && !stage_dense) {
+            f.direct = true;
+            std::sort(f.segs.begin(), f.segs.end(), [](const FileSpec::Seg& x, const FileSpec::Seg& y) { return x.off < y.off; });
+            direct_files.push_back(int(i));
+            job->stats.direct_bytes += f.nbytes;
+            continue;
+        }
         const uint64_t fb = align_up(f.nbytes, 256);
-        if (fb > cap) return set_err(TSNAP_ECUDA, "file larger than half of the staging arena: " + f.path);
-        if (job->waves.back().bytes + fb > cap) job->waves.emplace_back();
+        if (job->waves.empty() || job->waves.back().bytes + fb > cap) job->waves.emplace_back();
         Wave& w = job->waves.back();
         f.arena_off = w.bytes;
         f.wave = int(job->waves.size()) - 1;
         w.bytes += fb;
-        w.files.push_back(fi);
+        w.files.push_back(int(i));
     }
     for (size_t i = 0; i < job->waves.size(); ++i) job->waves[i].region_off = single ? 0 : (i % 2) * cap;
+    job->n_staged_waves = job->waves.size();
+    job->stats.n_waves = job->waves.size();
+    job->stats.arena_bytes = job->waves.empty() ? 0 : A;
+    if (!direct_files.empty()) {
+        job->waves.emplace_back();
+        Wave& w = job->waves.back();
+        w.direct = true;
+        w.files = direct_files;
+        for (int fi : direct_files) job->files[fi].wave = int(job->waves.size()) - 1;
+    }
     return TSNAP_OK;
 }
 
@@ -499,24 +615,82 @@ static bool direct_host_member(const FileSpec& f, bool save, Member* out) {
 static void finish_file_part(tsnap_job* job, FileSpec& f, uint64_t bytes_io, bool save) {
     if (save) job->eng->bytes_written += bytes_io;
     else job->eng->bytes_read += bytes_io;
-    if (f.parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1 && f.fd >= 0) {
-        if (save && (job->eng->cfg.flags & TSNAP_ENGINE_FSYNC)) fsync(f.fd);
-        close(f.fd);
-        f.fd = -1;
+    if (f.parts_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> g(f.open_mu);
+        if (f.fd >= 0) {
+            // O_DIRECT tails were written padded to a whole block: cut the file back to its size
+            if (save && f.direct_io && (f.nbytes & 4095) && ftruncate(f.fd, off_t(f.nbytes)) != 0)
+                job->fail(TSNAP_EIO, "ftruncate " + f.path + ": " + strerror(errno));
+            if (save && (job->eng->cfg.flags & TSNAP_ENGINE_FSYNC)) fsync(f.fd);
+            close(f.fd);
+            f.fd = -1;
+        }
     }
     job->part_done();
 }
 
-static int open_file(tsnap_job* job, FileSpec& f, bool save) {
-    if (save) {
-        if (make_parent_dirs(f.path) != 0) return set_err(TSNAP_EIO, "mkdir for " + f.path + ": " + strerror(errno));
-        f.fd = open(f.path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    } else {
-        f.fd = open(f.path.c_str(), O_RDONLY);
+// Files are opened by the worker that performs their first I/O and closed by the one that performs the last:
+// at most (workers + ring slots) descriptors are open at a time however many files the job has (the reference
+// keeps <= 16 I/Os in flight, T:knobs.py:38), and the creates overlap the drain instead of preceding it.
+static bool ensure_open(tsnap_job* job, FileSpec& f, bool save) {
+    std::lock_guard<std::mutex> g(f.open_mu);
+    if (f.opened) return !f.open_failed;
+    f.opened = true;
+    const double t0 = job->eng->trace ? job->now_ms() : 0;
+    if (save && make_parent_dirs(f.path) != 0) {
+        f.open_failed = true;
+        job->fail(TSNAP_EIO, "mkdir for " + f.path + ": " + strerror(errno));
+        return false;
     }
-    if (f.fd < 0) return set_err(TSNAP_EIO, "open " + f.path + ": " + strerror(errno));
-    (void)job;
-    return TSNAP_OK;
+    const int base = save ? (O_WRONLY | O_CREAT | O_TRUNC) : O_RDONLY;
+    // host-only files do their I/O from/to tensor memory of arbitrary alignment: always buffered
+    const bool want_direct = job->eng->odirect && !f.host_only;
+    if (want_direct) {
+        f.fd = open(f.path.c_str(), base | O_DIRECT, 0644);
+        f.direct_io = f.fd >= 0;
+    }
+    if (f.fd < 0) f.fd = open(f.path.c_str(), base, 0644);
+    if (f.fd < 0) {
+        f.open_failed = true;
+        job->fail(TSNAP_EIO, "open " + f.path + ": " + strerror(errno));
+        return false;
+    }
+    if (job->eng->trace) job->add_trace(TSNAP_TR_OPEN, g_lane, int(&f - &job->files[0]), t0, job->now_ms(), 0);
+    return true;
+}
+
+// one chunk of a file from a ring slot (capacity >= slot_bytes + slack, 4 KiB aligned)
+static int write_chunk(FileSpec& f, const char* slot, uint64_t n, uint64_t lo) {
+    if (!f.direct_io) return pwrite_all(f.fd, slot, n, lo);
+    // lo is a multiple of the slot size (a multiple of 4 KiB); only the last chunk of a file is ragged
+    return pwrite_all(f.fd, slot, align_up(n, 4096), lo);
+}
+// reads file bytes [off, off+n) into the slot; *skip = where they start inside it
+static int read_chunk(FileSpec& f, char* slot, uint64_t n, uint64_t off, uint64_t* skip) {
+    *skip = 0;
+    if (!f.direct_io) return pread_all(f.fd, slot, n, off);
+    const uint64_t a = off & ~uint64_t(4095);
+    const uint64_t want = align_up(off + n, 4096) - a;  // <= n + 8190 <= slot capacity
+    *skip = off - a;
+    uint64_t got = 0;
+    while (got < *skip + n) {
+        ssize_t r = pread(f.fd, slot + got, want - got, off_t(a + got));
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        if (r == 0) {
+            errno = ENODATA;
+            return -1;
+        }
+        got += uint64_t(r);
+        if (got & 4095) break;  // short read at the end of the file
+    }
+    if (got < *skip + n) {
+        errno = ENODATA;
+        return -1;
+    }
+    return 0;
 }
 
 // number of I/O parts a file contributes
@@ -538,16 +712,22 @@ static void post_host_file(tsnap_job* job, int fi, bool save) {
     FileSpec& f = job->files[fi];
     const uint64_t sb = eng->ring.slot_bytes();
     if (f.nbytes == 0) {
-        if (save) eng->io->post([job, &f] { finish_file_part(job, f, 0, true); });
+        if (save)
+            eng->io->post([job, &f] {
+                ensure_open(job, f, true);
+                finish_file_part(job, f, 0, true);
+            });
         return;
     }
     Member dm;
     if (save && direct_host_member(f, save, &dm)) {
         eng->io->post([job, &f, dm, sb] {
-            for (uint64_t lo = 0; lo < f.nbytes && !job->failed(); lo += sb) {
-                const uint64_t n = std::min<uint64_t>(sb, f.nbytes - lo);
-                if (pwrite_all(f.fd, reinterpret_cast<const char*>(uintptr_t(dm.src)) + lo, n, lo) != 0)
-                    job->fail(TSNAP_EIO, "pwrite " + f.path + ": " + strerror(errno));
+            if (!job->failed() && ensure_open(job, f, true)) {
+                for (uint64_t lo = 0; lo < f.nbytes && !job->failed(); lo += sb) {
+                    const uint64_t n = std::min<uint64_t>(sb, f.nbytes - lo);
+                    if (pwrite_all(f.fd, reinterpret_cast<const char*>(uintptr_t(dm.src)) + lo, n, lo) != 0)
+                        job->fail(TSNAP_EIO, "pwrite " + f.path + ": " + strerror(errno));
+                }
             }
             finish_file_part(job, f, f.nbytes, true);
         });
@@ -556,19 +736,18 @@ static void post_host_file(tsnap_job* job, int fi, bool save) {
     if (direct_host_member(f, save, &dm)) {
         for (uint64_t lo = 0; lo < f.nbytes; lo += sb) {
             const uint64_t n = std::min(sb, f.nbytes - lo);
-            eng->io->post([job, &f, dm, lo, n, save] {
-                if (!job->failed()) {
-                    int rc = save ? pwrite_all(f.fd, reinterpret_cast<const char*>(uintptr_t(dm.src)) + lo, n, lo)
-                                  : pread_all(f.fd, reinterpret_cast<char*>(uintptr_t(dm.dst)) + lo, n, f.offset + lo);
-                    if (rc != 0) job->fail(TSNAP_EIO, (save ? "pwrite " : "pread ") + f.path + ": " + strerror(errno));
+            eng->io->post([job, &f, dm, lo, n] {
+                if (!job->failed() && ensure_open(job, f, false)) {
+                    if (pread_all(f.fd, reinterpret_cast<char*>(uintptr_t(dm.dst)) + lo, n, f.offset + lo) != 0)
+                        job->fail(TSNAP_EIO, "pread " + f.path + ": " + strerror(errno));
                 }
-                finish_file_part(job, f, n, save);
+                finish_file_part(job, f, n, false);
             });
         }
         return;
     }
     eng->io->post([job, &f, save] {
-        if (!job->failed()) {
+        if (!job->failed() && ensure_open(job, f, save)) {
             char* tmp = static_cast<char*>(malloc(f.nbytes));
             if (!tmp) {
                 job->fail(TSNAP_ENOMEM, "malloc of a host slab failed");
@@ -615,12 +794,30 @@ static void account_parts(tsnap_job* job, int64_t async_parts) {
     job->accounted = true;
 }
 
+// payload memcpys of chunk [lo, lo+n) of a direct file: one per dense run that intersects it
+static bool direct_chunk_copies(tsnap_job* job, const FileSpec& f, char* slot, uint64_t lo, uint64_t n, bool to_host) {
+    tsnap_engine* eng = job->eng;
+    size_t i = size_t(std::upper_bound(f.segs.begin(), f.segs.end(), lo, [](uint64_t v, const FileSpec::Seg& s) { return v < s.off + s.bytes; }) - f.segs.begin());
+    bool ok = true;
+    for (; ok && i < f.segs.size() && f.segs[i].off < lo + n; ++i) {
+        const FileSpec::Seg& sg = f.segs[i];
+        const uint64_t a = std::max(lo, sg.off), b = std::min(lo + n, sg.off + sg.bytes);
+        if (a >= b) continue;
+        char* dev = reinterpret_cast<char*>(uintptr_t(sg.addr)) + (a - sg.off);
+        ok = to_host ? cudaMemcpyAsync(slot + (a - lo), dev, b - a, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess
+                     : cudaMemcpyAsync(dev, slot + (a - lo), b - a, cudaMemcpyHostToDevice, eng->s_copy) == cudaSuccess;
+        job->n_memcpy.fetch_add(1, std::memory_order_relaxed);
+    }
+    return ok;
+}
+
 static int run_save_inner(tsnap_job* job) {
     NvtxRange nvtx_job("tsnap:save_job issue (plan, pack launch, D2H issue)");
     tsnap_engine* eng = job->eng;
     int rc = ensure_ring(eng);
     if (rc != TSNAP_OK) return rc;
     auto t0 = clk::now();
+    const double tr0 = job->now_ms();
     rc = build_waves(job);
     if (rc != TSNAP_OK) return rc;
     for (Wave& w : job->waves) {
@@ -628,13 +825,16 @@ static int run_save_inner(tsnap_job* job) {
         if (rc != TSNAP_OK) return rc;
     }
     job->stats.plan_ms = ms_since(t0);
-    // The first waves' pack kernels go out before anything else: they run while the files are created, which
-    // takes the file creates (~8 ms for 132 files) out of the async_take blocking window.  Nothing asynchronous
-    // references the job yet, so a failure below only has to drain the stream before returning.
+    if (eng->trace) job->add_trace(TSNAP_TR_PLAN, 0, -1, tr0, job->now_ms(), 0);
+    // The first waves' pack kernels go out before anything else: they run while the rest of the job is set up,
+    // which keeps the async_take blocking window at plan + pack.  Nothing asynchronous references the job yet,
+    // so a failure below only has to drain the stream before returning.
     const size_t nw = job->waves.size();
+    const size_t ns = job->n_staged_waves;
+    const bool has_direct = nw > ns;
     size_t launched = 0;
-    for (; launched < std::min<size_t>(2, nw); ++launched) {
-        if (launched == 0 && job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
+    if (job->ev_producer && ns > 0) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
+    for (; launched < std::min<size_t>(2, ns); ++launched) {
         rc = launch_wave(job, job->waves[launched]);
         if (rc != TSNAP_OK) {
             cudaStreamSynchronize(eng->s_kernel);
@@ -646,52 +846,64 @@ static int run_save_inner(tsnap_job* job) {
         cudaStreamSynchronize(eng->s_kernel);
         return set_err(code, msg);
     };
-    // open every file and compute the part count before anything can complete
+    // part count of every file before anything can complete (files are opened by the workers, see ensure_open)
     int64_t parts = 0;
     for (FileSpec& f : job->files) {
-        rc = open_file(job, f, true);
-        if (rc != TSNAP_OK) return bail(rc);
         const int64_t p = count_parts(eng, f, true);
         f.parts_left.store(p);
         parts += p;
     }
     for (Wave& w : job->waves)
         if (cudaEventCreateWithFlags(&w.ev_copied, cudaEventDisableTiming) != cudaSuccess) return bail(set_err(TSNAP_ECUDA, "event create failed"));
-    if (!job->waves.empty()) {
+    if (nw > 0) {
         if (cudaEventCreate(&job->ev_copy_begin) != cudaSuccess || cudaEventCreate(&job->ev_copy_end) != cudaSuccess)
             return bail(set_err(TSNAP_ECUDA, "event create failed"));
     }
     account_parts(job, parts);
-    if (job->waves.empty()) mark_device_done(job);
+    if (nw == 0) mark_device_done(job);
     if (parts == 0) return TSNAP_OK;
 
-    auto arm_device_done = [&](Wave& w) {
-        push_pending(eng, w.ev_done, [job](bool ok) {
+    // Sources are reusable (the async_take gate) once the last pack kernel has finished and, when files are drained
+    // straight from the live tensors, once the last of those copies has finished.
+    auto arm_kernel_done = [&](Wave& w, size_t wi, bool gate) {
+        Wave* wp = &w;
+        push_pending(eng, w.ev_done, [job, wp, wi, gate, eng](bool ok) {
             if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
-            mark_device_done(job);
+            if (eng->trace) {
+                collect_wave_timing(job, *wp);
+                const double t1 = job->now_ms();
+                job->add_trace(TSNAP_TR_KERNEL, int(wi), -1, t1 - wp->kernel_ms, t1, wp->bytes);
+            }
+            if (gate) mark_device_done(job);
         });
     };
-    if (nw > 0 && launched == nw) arm_device_done(job->waves[nw - 1]);
+    for (size_t wi = 0; wi < launched; ++wi) {
+        const bool gate = !has_direct && wi + 1 == ns;
+        if (gate || eng->trace) arm_kernel_done(job->waves[wi], wi, gate);
+    }
     auto launch_next = [&]() -> int {
         Wave& w = job->waves[launched];
         if (launched >= 2) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->waves[launched - 2].ev_copied, 0));
         int r = launch_wave(job, w);
         if (r != TSNAP_OK) return r;
+        const bool gate = !has_direct && launched + 1 == ns;
+        if (gate || eng->trace) arm_kernel_done(w, launched, gate);
         ++launched;
-        if (launched == nw) arm_device_done(w);
         return TSNAP_OK;
     };
     // host-only files go straight to the I/O workers
     for (size_t i = 0; i < job->files.size(); ++i) {
         FileSpec& f = job->files[i];
-        if (f.host_only || f.nbytes == 0) {
-            post_host_file(job, int(i), true);
-        }
+        if (f.host_only || f.nbytes == 0) post_host_file(job, int(i), true);
     }
     const uint64_t sb = eng->ring.slot_bytes();
+    static const bool dbg_skip_d2h = getenv("TSNAP_B200_DEBUG_SKIP_D2H") != nullptr;      // experiments only
+    static const bool dbg_skip_write = getenv("TSNAP_B200_DEBUG_SKIP_WRITE") != nullptr;  // experiments only
     for (size_t wi = 0; wi < nw; ++wi) {
         Wave& w = job->waves[wi];
-        bool ok = cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0) == cudaSuccess;
+        bool ok;
+        if (w.direct) ok = !job->ev_producer || cudaStreamWaitEvent(eng->s_copy, job->ev_producer, 0) == cudaSuccess;
+        else ok = cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0) == cudaSuccess;
         if (wi == 0) cudaEventRecord(job->ev_copy_begin, eng->s_copy);
         // Buffered writes take the inode lock exclusively, so two chunks of one file never make progress at
         // the same time.  Treat every file as a sequential job and spread its chunks evenly over the whole
@@ -712,42 +924,63 @@ static int run_save_inner(tsnap_job* job) {
         std::stable_sort(order.begin(), order.end(), [](const ChunkRef& x, const ChunkRef& y) { return x.due < y.due; });
         for (const ChunkRef& cr : order) {
             FileSpec& f = job->files[cr.fi];
-            const char* base = eng->arena + w.region_off + f.arena_off;
-            {
-                const uint64_t lo = cr.lo;
-                const uint64_t n = std::min(sb, f.nbytes - lo);
-                auto tw = clk::now();
-                char* slot = eng->ring.acquire();
-                job->slot_wait_us += int64_t(ms_since(tw) * 1000.0);
-                cudaEvent_t ev = eng->get_event();
-                static const bool dbg_skip_d2h = getenv("TSNAP_B200_DEBUG_SKIP_D2H") != nullptr;  // experiments only
-                ok = ok && !job->failed() &&
-                     (dbg_skip_d2h || cudaMemcpyAsync(slot, base + lo, n, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess) &&
-                     cudaEventRecord(ev, eng->s_copy) == cudaSuccess;
-                if (!ok) job->fail(TSNAP_ECUDA, std::string("D2H copy: ") + cudaGetErrorString(cudaGetLastError()));
-                eng->bytes_d2h += n;
-                FileSpec* fp = &f;
-                push_pending(eng, ev, [eng, job, fp, slot, lo, n, ev](bool evok) {
-                    eng->put_event(ev);
-                    if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
-                    auto tq = clk::now();
-                    eng->io->post([eng, job, fp, slot, lo, n, tq] {
-                        job->io_queue_us += int64_t(ms_since(tq) * 1000.0);
-                        NvtxRange nvtx_w("tsnap:pwrite chunk");
-                        auto tb = clk::now();
-                        static const bool dbg_skip_write = getenv("TSNAP_B200_DEBUG_SKIP_WRITE") != nullptr;  // experiments only
-                        if (!dbg_skip_write && !job->failed() && pwrite_all(fp->fd, slot, n, lo) != 0)
-                            job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
-                        job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
-                        eng->ring.release(slot);
-                        finish_file_part(job, *fp, n, true);
-                    });
-                });
+            const uint64_t lo = cr.lo;
+            const uint64_t n = std::min(sb, f.nbytes - lo);
+            auto tw = clk::now();
+            const double tw_ms = eng->trace ? job->now_ms() : 0;
+            char* slot = eng->ring.acquire();
+            const double waited = ms_since(tw);
+            job->slot_wait_us += int64_t(waited * 1000.0);
+            if (eng->trace && waited > 0.05) job->add_trace(TSNAP_TR_SLOT_WAIT, 0, cr.fi, tw_ms, job->now_ms(), 0);
+            cudaEvent_t ev = eng->get_event();
+            const double t_issue = eng->trace ? job->now_ms() : 0;
+            if (ok && !job->failed() && !dbg_skip_d2h) {
+                if (w.direct) {
+                    ok = direct_chunk_copies(job, f, slot, lo, n, true);
+                } else {
+                    ok = cudaMemcpyAsync(slot, job->arena + w.region_off + f.arena_off + lo, n, cudaMemcpyDeviceToHost, eng->s_copy) == cudaSuccess;
+                    job->n_memcpy.fetch_add(1, std::memory_order_relaxed);
+                }
             }
+            ok = ok && cudaEventRecord(ev, eng->s_copy) == cudaSuccess;
+            if (!ok) job->fail(TSNAP_ECUDA, std::string("D2H copy: ") + cudaGetErrorString(cudaGetLastError()));
+            eng->bytes_d2h += n;
+            FileSpec* fp = &f;
+            const int fidx = cr.fi;
+            push_pending(eng, ev, [eng, job, fp, fidx, slot, lo, n, ev, t_issue](bool evok) {
+                eng->put_event(ev);
+                if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
+                if (eng->trace) {
+                    // the copy engine runs the chunks of s_copy back to back: busy since the later of "issued" and
+                    // "previous chunk done"
+                    const double t1 = job->now_ms();
+                    job->add_trace(TSNAP_TR_D2H, 0, fidx, std::max(t_issue, job->last_copy_done_ms), t1, n);
+                    job->last_copy_done_ms = t1;
+                }
+                auto tq = clk::now();
+                eng->io->post([eng, job, fp, fidx, slot, lo, n, tq] {
+                    job->io_queue_us += int64_t(ms_since(tq) * 1000.0);
+                    NvtxRange nvtx_w("tsnap:pwrite chunk");
+                    if (!dbg_skip_write && !job->failed() && ensure_open(job, *fp, true)) {
+                        auto tb = clk::now();
+                        const double t0w = eng->trace ? job->now_ms() : 0;
+                        if (write_chunk(*fp, slot, n, lo) != 0) job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
+                        job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
+                        if (eng->trace) job->add_trace(TSNAP_TR_PWRITE, g_lane, fidx, t0w, job->now_ms(), n);
+                    }
+                    eng->ring.release(slot);
+                    finish_file_part(job, *fp, n, true);
+                });
+            });
         }
         if (wi + 1 == nw) cudaEventRecord(job->ev_copy_end, eng->s_copy);
         if (cudaEventRecord(w.ev_copied, eng->s_copy) != cudaSuccess) job->fail(TSNAP_ECUDA, "event record failed");
-        if (launched < nw) {
+        if (w.direct)
+            push_pending(eng, w.ev_copied, [job](bool evok) {
+                if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
+                mark_device_done(job);
+            });
+        if (launched < ns) {
             rc = launch_next();
             if (rc != TSNAP_OK) {
                 job->fail(rc, last_err());
@@ -777,6 +1010,7 @@ static int run_load_inner(tsnap_job* job) {
     int rc = ensure_ring(eng);
     if (rc != TSNAP_OK) return rc;
     auto t0 = clk::now();
+    const double tr0 = job->now_ms();
     rc = build_waves(job);
     if (rc != TSNAP_OK) return rc;
     for (Wave& w : job->waves) {
@@ -784,14 +1018,11 @@ static int run_load_inner(tsnap_job* job) {
         if (rc != TSNAP_OK) return rc;
     }
     job->stats.plan_ms = ms_since(t0);
+    if (eng->trace) job->add_trace(TSNAP_TR_PLAN, 0, -1, tr0, job->now_ms(), 0);
     const uint64_t sb = eng->ring.slot_bytes();
     int64_t parts = 0;
     for (FileSpec& f : job->files) {
         if (f.nbytes == 0) continue;
-        if (!f.mem_src) {
-            rc = open_file(job, f, false);
-            if (rc != TSNAP_OK) return rc;
-        }
         const int64_t p = count_parts(eng, f, false);
         f.parts_left.store(p);
         parts += p;
@@ -810,12 +1041,21 @@ static int run_load_inner(tsnap_job* job) {
     for (size_t i = 0; i < job->files.size(); ++i)
         if (job->files[i].host_only && job->files[i].nbytes) post_host_file(job, int(i), false);
 
+    // Everything that writes destination tensors is ordered after the work already queued on the caller's stream:
+    // the scatter kernels (s_kernel) and, for files uploaded straight into the live tensors, the copies (s_copy).
+    bool any_direct = false;
+    for (Wave& w : job->waves) any_direct = any_direct || w.direct;
+    if (job->ev_consumer) {
+        if (job->n_staged_waves) cudaStreamWaitEvent(eng->s_kernel, job->ev_consumer, 0);
+        if (any_direct) cudaStreamWaitEvent(eng->s_copy, job->ev_consumer, 0);
+    }
+
     auto shared = std::make_shared<LoadShared>();
     shared->launched.assign(job->waves.size(), 0);
     const size_t nw = job->waves.size();
     for (size_t wi = 0; wi < nw; ++wi) {
         Wave* w = &job->waves[wi];
-        if (wi >= 2) {
+        if (!w->direct && wi >= 2) {
             // the region is reused: wait until the scatter of wave wi-2 has been enqueued, then order
             // this wave's uploads after it on the device
             std::unique_lock<std::mutex> g(shared->mu);
@@ -827,30 +1067,54 @@ static int run_load_inner(tsnap_job* job) {
         const bool last_wave = (wi + 1 == nw);
         for (int fi : w->files) {
             FileSpec* f = &job->files[fi];
-            char* base = eng->arena + w->region_off + f->arena_off;
+            char* base = w->direct ? nullptr : job->arena + w->region_off + f->arena_off;
             for (uint64_t lo = 0; lo < f->nbytes; lo += sb) {
                 const uint64_t n = std::min(sb, f->nbytes - lo);
                 char* slot = eng->ring.acquire();
-                eng->io->post([eng, job, w, wi, f, base, slot, lo, n, shared, last_wave] {
+                eng->io->post([eng, job, w, wi, f, fi, base, slot, lo, n, shared, last_wave] {
                     NvtxRange nvtx_r("tsnap:pread chunk + H2D enqueue");
                     cudaSetDevice(eng->device);
                     bool ok = !job->failed();
+                    uint64_t skip = 0;
+                    const double t0r = eng->trace ? job->now_ms() : 0;
                     if (ok && f->mem_src) {
                         memcpy(slot, f->mem_src + lo, n);
-                    } else if (ok && pread_all(f->fd, slot, n, f->offset + lo) != 0) {
-                        job->fail(TSNAP_EIO, "pread " + f->path + ": " + strerror(errno));
-                        ok = false;
+                    } else if (ok) {
+                        auto tb = clk::now();
+                        if (!ensure_open(job, *f, false)) {
+                            ok = false;
+                        } else if (read_chunk(*f, slot, n, f->offset + lo, &skip) != 0) {
+                            job->fail(TSNAP_EIO, "pread " + f->path + ": " + strerror(errno));
+                            ok = false;
+                        }
+                        job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
                     }
+                    const double t_issue = eng->trace ? job->now_ms() : 0;
+                    if (eng->trace) job->add_trace(TSNAP_TR_PREAD, g_lane, fi, t0r, t_issue, n);
                     cudaEvent_t ev = eng->get_event();
-                    if (ok && cudaMemcpyAsync(base + lo, slot, n, cudaMemcpyHostToDevice, eng->s_copy) != cudaSuccess) {
-                        job->fail(TSNAP_ECUDA, "H2D copy failed to enqueue");
-                        ok = false;
+                    if (ok) {
+                        bool cok;
+                        if (w->direct) {
+                            cok = direct_chunk_copies(job, *f, slot + skip, lo, n, false);
+                        } else {
+                            cok = cudaMemcpyAsync(base + lo, slot + skip, n, cudaMemcpyHostToDevice, eng->s_copy) == cudaSuccess;
+                            job->n_memcpy.fetch_add(1, std::memory_order_relaxed);
+                        }
+                        if (!cok) {
+                            job->fail(TSNAP_ECUDA, "H2D copy failed to enqueue");
+                            ok = false;
+                        }
                     }
                     cudaEventRecord(ev, eng->s_copy);
                     eng->bytes_h2d += n;
-                    push_pending(eng, ev, [eng, job, f, slot, n, ev](bool evok) {
+                    push_pending(eng, ev, [eng, job, f, fi, slot, n, ev, t_issue](bool evok) {
                         eng->put_event(ev);
                         if (!evok) job->fail(TSNAP_ECUDA, "H2D copy failed");
+                        if (eng->trace) {
+                            const double t1 = job->now_ms();
+                            job->add_trace(TSNAP_TR_H2D, 0, fi, std::max(t_issue, job->last_copy_done_ms), t1, n);
+                            job->last_copy_done_ms = t1;
+                        }
                         eng->ring.release(slot);
                         finish_file_part(job, *f, n, false);
                     });
@@ -860,9 +1124,15 @@ static int run_load_inner(tsnap_job* job) {
                         if (!job->failed()) {
                             cudaEventCreateWithFlags(&w->ev_copied, cudaEventDisableTiming);
                             cudaEventRecord(w->ev_copied, eng->s_copy);
-                            cudaStreamWaitEvent(eng->s_kernel, w->ev_copied, 0);
-                            r = launch_wave(job, *w);
-                            if (r != TSNAP_OK) job->fail(r, last_err());
+                            if (w->direct) {
+                                // no scatter: the uploads were the restore
+                                cudaEventCreateWithFlags(&w->ev_done, cudaEventDisableTiming);
+                                cudaEventRecord(w->ev_done, eng->s_copy);
+                            } else {
+                                cudaStreamWaitEvent(eng->s_kernel, w->ev_copied, 0);
+                                r = launch_wave(job, *w);
+                                if (r != TSNAP_OK) job->fail(r, last_err());
+                            }
                         }
                         {
                             std::lock_guard<std::mutex> g(shared->mu);
@@ -870,9 +1140,13 @@ static int run_load_inner(tsnap_job* job) {
                         }
                         shared->cv.notify_all();
                         if (r == TSNAP_OK && w->ev_done && !job->failed()) {
-                            push_pending(eng, w->ev_done, [job, w, last_wave](bool evok) {
+                            push_pending(eng, w->ev_done, [eng, job, w, wi, last_wave](bool evok) {
                                 if (!evok) job->fail(TSNAP_ECUDA, "scatter kernel failed");
                                 collect_wave_timing(job, *w);
+                                if (eng->trace && !w->direct) {
+                                    const double t1 = job->now_ms();
+                                    job->add_trace(TSNAP_TR_KERNEL, int(wi), -1, t1 - w->kernel_ms, t1, w->bytes);
+                                }
                                 if (last_wave) mark_device_done(job);
                                 job->part_done();
                             });
@@ -924,41 +1198,56 @@ static int run_stage_inner(tsnap_job* job) {
     rc = plan_wave(job, w);
     if (rc != TSNAP_OK) return rc;
     job->stats.plan_ms = ms_since(t0);
-    if (job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
-    rc = launch_wave(job, w);
-    if (rc != TSNAP_OK) return rc;
-    CUDA_TRY(cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0));
     CUDA_TRY(cudaEventCreate(&job->ev_copy_begin));
     CUDA_TRY(cudaEventCreate(&job->ev_copy_end));
-    CUDA_TRY(cudaEventRecord(job->ev_copy_begin, eng->s_copy));
-    const char* base = eng->arena + w.region_off + f.arena_off;
     char* out = static_cast<char*>(job->stage_buf);
-    if (!mixed) {
-        CUDA_TRY(cudaMemcpyAsync(out, base, f.nbytes, cudaMemcpyDeviceToHost, eng->s_copy));
-        eng->bytes_d2h += f.nbytes;
+    Wave* wp = &w;
+    if (w.direct) {
+        // no HBM staging available: dense members go straight from the live tensors into the pinned buffer
+        if (job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_copy, job->ev_producer, 0));
+        CUDA_TRY(cudaEventRecord(job->ev_copy_begin, eng->s_copy));
+        for (const FileSpec::Seg& sg : f.segs) {
+            CUDA_TRY(cudaMemcpyAsync(out + sg.off, reinterpret_cast<const void*>(uintptr_t(sg.addr)), sg.bytes, cudaMemcpyDeviceToHost, eng->s_copy));
+            eng->bytes_d2h += sg.bytes;
+            job->n_memcpy.fetch_add(1, std::memory_order_relaxed);
+        }
     } else {
-        for (const tsnap_copy_desc& d : dev) {
-            uint64_t numel = 1;
-            for (int i = 0; i < d.ndim; ++i) numel *= uint64_t(d.sizes[i]);
-            const uint64_t nb = numel * dtype_size(d.dst_dtype);
-            if (nb == 0) continue;
-            CUDA_TRY(cudaMemcpyAsync(out + d.dst_addr, base + d.dst_addr, nb, cudaMemcpyDeviceToHost, eng->s_copy));
-            eng->bytes_d2h += nb;
+        if (job->ev_producer) CUDA_TRY(cudaStreamWaitEvent(eng->s_kernel, job->ev_producer, 0));
+        rc = launch_wave(job, w);
+        if (rc != TSNAP_OK) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(eng->s_copy, w.ev_done, 0));
+        CUDA_TRY(cudaEventRecord(job->ev_copy_begin, eng->s_copy));
+        const char* base = job->arena + w.region_off + f.arena_off;
+        if (!mixed) {
+            CUDA_TRY(cudaMemcpyAsync(out, base, f.nbytes, cudaMemcpyDeviceToHost, eng->s_copy));
+            eng->bytes_d2h += f.nbytes;
+            job->n_memcpy.fetch_add(1, std::memory_order_relaxed);
+        } else {
+            for (const tsnap_copy_desc& d : dev) {
+                uint64_t numel = 1;
+                for (int i = 0; i < d.ndim; ++i) numel *= uint64_t(d.sizes[i]);
+                const uint64_t nb = numel * dtype_size(d.dst_dtype);
+                if (nb == 0) continue;
+                CUDA_TRY(cudaMemcpyAsync(out + d.dst_addr, base + d.dst_addr, nb, cudaMemcpyDeviceToHost, eng->s_copy));
+                eng->bytes_d2h += nb;
+                job->n_memcpy.fetch_add(1, std::memory_order_relaxed);
+            }
         }
     }
     CUDA_TRY(cudaEventRecord(job->ev_copy_end, eng->s_copy));
     cudaEvent_t ev = eng->get_event();
     CUDA_TRY(cudaEventRecord(ev, eng->s_copy));
-    Wave* wp = &w;
     account_parts(job, 1);
-    push_pending(eng, w.ev_done, [job](bool ok) {
-        if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
-        mark_device_done(job);
-    });
+    if (!w.direct)
+        push_pending(eng, w.ev_done, [job](bool ok) {
+            if (!ok) job->fail(TSNAP_ECUDA, "pack kernel failed");
+            mark_device_done(job);
+        });
     push_pending(eng, ev, [eng, job, ev, wp](bool ok) {
         eng->put_event(ev);
         if (!ok) job->fail(TSNAP_ECUDA, "D2H copy failed");
         collect_wave_timing(job, *wp);
+        mark_device_done(job);
         job->part_done();
     });
     return TSNAP_OK;
@@ -971,7 +1260,7 @@ static void run_job(tsnap_job* job) {
     // at a time: a job that touches the GPU waits here until its predecessor has completely drained.
     bool device_job = job->kind == kStage;
     for (const FileSpec& f : job->files) device_job = device_job || (!f.host_only && f.nbytes > 0);
-    if (device_job && eng->has_device) {
+    if (device_job && eng->has_device && !job->arena_set && !eng->no_arena) {
         std::unique_lock<std::mutex> ga(eng->arena_mu);
         eng->arena_cv.wait(ga, [eng] { return !eng->arena_in_use; });
         eng->arena_in_use = true;
@@ -986,11 +1275,6 @@ static void run_job(tsnap_job* job) {
         mark_device_done(job);
         if (!job->accounted) {
             // failed before any asynchronous part was handed out
-            for (FileSpec& f : job->files)
-                if (f.fd >= 0) {
-                    close(f.fd);
-                    f.fd = -1;
-                }
             account_parts(job, 0);
         }
     }
@@ -1019,7 +1303,20 @@ static void drain_main(tsnap_engine* eng) {
             std::unique_lock<std::mutex> g(eng->q_mu);
             eng->busy = false;
             eng->q_cv.notify_all();
-            eng->q_cv.wait(g, [eng] { return eng->stopping || !eng->job_q.empty() || eng->trim_arena; });
+            // An engine-owned arena is given back once the engine has been idle for a moment (it is invisible to the
+            // host runtime's allocator, so holding it across training steps can OOM them); TSNAP_B200_KEEP_ARENA=1 keeps
+            // it for back-to-back snapshots.
+            while (!(eng->stopping || !eng->job_q.empty() || eng->trim_arena)) {
+                if (eng->arena && !eng->keep_arena && eng->active_jobs.load(std::memory_order_acquire) == 0) {
+                    if (eng->q_cv.wait_for(g, std::chrono::milliseconds(50)) == std::cv_status::timeout && eng->job_q.empty() &&
+                        !eng->stopping && eng->active_jobs.load(std::memory_order_acquire) == 0)
+                        eng->trim_arena = true;
+                } else if (eng->arena && !eng->keep_arena) {
+                    eng->q_cv.wait_for(g, std::chrono::milliseconds(5));
+                } else {
+                    eng->q_cv.wait(g);
+                }
+            }
             if (eng->trim_arena && eng->job_q.empty()) {
                 g.unlock();
                 free_arena(eng);
@@ -1034,7 +1331,6 @@ static void drain_main(tsnap_engine* eng) {
             eng->busy = true;
         }
         run_job(job);
-        if (eng->release_arena_after_job && eng->has_device) free_arena(eng);
     }
 }
 
@@ -1053,6 +1349,17 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
     eng->cfg = *cfg;
     eng->device = cfg->device;
     eng->allow_bulk = !(cfg->flags & TSNAP_ENGINE_NO_BULK);
+    eng->trace = (cfg->flags & TSNAP_ENGINE_TRACE) != 0;
+    eng->odirect = (cfg->flags & TSNAP_ENGINE_ODIRECT) != 0;
+    eng->no_arena = (cfg->flags & TSNAP_ENGINE_NO_ARENA) != 0;
+    {
+        // one descriptor per in-flight chunk at most, but leave room for the host process: lift the soft limit
+        struct rlimit rl;
+        if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) {
+            rl.rlim_cur = rl.rlim_max == RLIM_INFINITY ? std::max<rlim_t>(rl.rlim_cur, 65536) : rl.rlim_max;
+            setrlimit(RLIMIT_NOFILE, &rl);
+        }
+    }
     if (cfg->device >= 0) {
         cudaError_t e = cudaSetDevice(cfg->device);
         cudaDeviceProp prop;
@@ -1073,11 +1380,16 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
         eng->sm_count = prop.multiProcessorCount;
         eng->has_device = true;
         eng->numa_cpus = gpu_numa_cpus(cfg->device);
-        const char* rel = getenv("TSNAP_B200_RELEASE_ARENA");
-        eng->release_arena_after_job = rel && rel[0] == '1';
+        const char* keep = getenv("TSNAP_B200_KEEP_ARENA");
+        eng->keep_arena = keep && keep[0] == '1';
         eng->completion_thread = std::thread(completion_main, eng);
     }
-    eng->io = new WorkerPool(cfg->io_threads > 0 ? cfg->io_threads : 16, eng->numa_cpus);
+    {
+        const int nio = cfg->io_threads > 0 ? cfg->io_threads : 16;
+        std::vector<std::vector<int>> placement = io_worker_cpus(nio, eng->numa_cpus);
+        if (placement.empty() && !eng->numa_cpus.empty()) placement.push_back(eng->numa_cpus);  // TSNAP_B200_NUMA=1
+        eng->io = new WorkerPool(nio, placement);
+    }
     eng->drain_thread = std::thread(drain_main, eng);
     *out = eng;
     return TSNAP_OK;
@@ -1170,6 +1482,7 @@ static int add_file(tsnap_job* job, const char* path, uint64_t offset, uint64_t 
     f.path = path;
     f.offset = offset;
     f.nbytes = nbytes;
+    f.dense = true;
     *idx = int32_t(job->files.size()) - 1;
     return TSNAP_OK;
 }
@@ -1206,6 +1519,14 @@ static int add_member(tsnap_job* job, int32_t fi, const tsnap_copy_desc* d, bool
         for (int i = 0; i < d->ndim; ++i)
             last += uint64_t(d->sizes[i] - 1) * uint64_t(d->src_strides[i]) * dtype_size(d->src_dtype);
         if (last + dtype_size(d->src_dtype) > f.nbytes) return set_err(TSNAP_EINVAL, "member reads past the byte range");
+    }
+    // dense, cast-free device members can be drained / uploaded without staging: remember their runs
+    const int tensor_space = save ? d->src_space : d->dst_space;
+    if (numel && tensor_space == TSNAP_SPACE_DEVICE) {
+        if (nc.n == 1 && nc.m[0].mode == kModeContig)
+            f.segs.push_back(FileSpec::Seg{save ? nc.m[0].dst : nc.m[0].src, save ? nc.m[0].src : nc.m[0].dst, nc.m[0].bytes});
+        else
+            f.dense = false;
     }
     f.members.push_back(*d);
     job->stats.n_members++;
@@ -1253,7 +1574,15 @@ static int submit(tsnap_job* job, void* stream, bool is_consumer) {
         CUDA_TRY(cudaEventCreateWithFlags(&job->ev_producer, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(job->ev_producer, static_cast<cudaStream_t>(stream)));
     }
-    if (is_consumer) job->consumer_stream = stream;
+    if (is_consumer) {
+        job->consumer_stream = stream;
+        if (any_device) {
+            // restored bytes must not be overtaken by work already queued on the caller's stream
+            cudaSetDevice(eng->device);
+            CUDA_TRY(cudaEventCreateWithFlags(&job->ev_consumer, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(job->ev_consumer, static_cast<cudaStream_t>(stream)));
+        }
+    }
     job->submitted = true;
     job->t_submit = clk::now();
     eng->active_jobs.fetch_add(1, std::memory_order_acq_rel);
@@ -1319,6 +1648,7 @@ int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out) {
     job->stats.slot_wait_ms = job->slot_wait_us.load() / 1000.0;
     job->stats.io_busy_ms = job->io_busy_us.load() / 1000.0;
     job->stats.io_queue_ms = job->io_queue_us.load() / 1000.0;
+    job->stats.n_memcpy = uint64_t(job->n_memcpy.load());
     *out = job->stats;
     return TSNAP_OK;
 }
@@ -1337,11 +1667,146 @@ int tsnap_job_destroy(tsnap_job* job) {
         if (w.ev_copied) cudaEventDestroy(w.ev_copied);
     }
     if (job->ev_producer) cudaEventDestroy(job->ev_producer);
+    if (job->ev_consumer) cudaEventDestroy(job->ev_consumer);
     if (job->ev_copy_begin) cudaEventDestroy(job->ev_copy_begin);
     if (job->ev_copy_end) cudaEventDestroy(job->ev_copy_end);
     for (FileSpec& f : job->files)
         if (f.fd >= 0) close(f.fd);
     delete job;
+    return TSNAP_OK;
+}
+
+// ---- caller-supplied arena, timeline, probes ------------------------------------------------------------------
+int tsnap_job_arena_hint(tsnap_job* job, tsnap_arena_hint* out) {
+    if (!job || !out) return set_err(TSNAP_EINVAL, "null argument");
+    // host_only is only known at submit: recompute from the members
+    ArenaNeed n;
+    for (const FileSpec& f : job->files) {
+        if (f.nbytes == 0) continue;
+        bool device = false;
+        for (const tsnap_copy_desc& d : f.members)
+            device = device || (job->kind == kLoad ? d.dst_space : d.src_space) == TSNAP_SPACE_DEVICE;
+        if (!device) continue;
+        const uint64_t fb = align_up(f.nbytes, 256);
+        n.total += fb;
+        n.largest = std::max(n.largest, fb);
+        if (!f.dense) {
+            n.nd_total += fb;
+            n.nd_largest = std::max(n.nd_largest, fb);
+        }
+    }
+    out->total_bytes = n.total;
+    out->largest_file_bytes = n.largest;
+    out->strided_total_bytes = n.nd_total;
+    out->strided_largest_bytes = n.nd_largest;
+    return TSNAP_OK;
+}
+int tsnap_job_set_arena(tsnap_job* job, void* device_ptr, uint64_t nbytes) {
+    if (!job) return set_err(TSNAP_EINVAL, "null job");
+    if (job->submitted) return set_err(TSNAP_ESTATE, "job already submitted");
+    if (nbytes && !device_ptr) return set_err(TSNAP_EINVAL, "null arena");
+    if (uintptr_t(device_ptr) & 255) return set_err(TSNAP_EINVAL, "the arena must be 256 B aligned");
+    job->arena = static_cast<char*>(device_ptr);
+    job->arena_bytes = nbytes / 512 * 512;  // two equal 256 B-aligned halves
+    job->arena_set = true;
+    return TSNAP_OK;
+}
+
+int tsnap_job_get_trace(tsnap_job* job, tsnap_trace_rec* out, uint64_t cap, uint64_t* n) {
+    if (!job || !n) return set_err(TSNAP_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(job->trace_mu);
+    *n = job->trace.size();
+    if (out)
+        for (uint64_t i = 0; i < cap && i < job->trace.size(); ++i) out[i] = job->trace[i];
+    return TSNAP_OK;
+}
+
+int tsnap_engine_probe(tsnap_engine* eng, int kind, const char* dir, uint64_t bytes, double* out_gbs) {
+    if (!eng || !out_gbs) return set_err(TSNAP_EINVAL, "null argument");
+    int rc = ensure_ring(eng);
+    if (rc != TSNAP_OK) return rc;
+    const uint64_t sb = eng->ring.slot_bytes();
+    const uint64_t chunks = std::max<uint64_t>(1, bytes / sb);
+    if (kind == TSNAP_PROBE_D2H || kind == TSNAP_PROBE_H2D) {
+        if (!eng->has_device) return set_err(TSNAP_ECUDA, "link probe on a host-only engine");
+        cudaSetDevice(eng->device);
+        const int depth = std::min<int>(eng->ring.count(), 8);
+        char* dev = nullptr;
+        CUDA_TRY(cudaMalloc(&dev, sb * depth));
+        std::vector<char*> slots;
+        for (int i = 0; i < depth; ++i) slots.push_back(eng->ring.acquire());
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int pass = 0; pass < 2; ++pass) {  // pass 0 warms the path
+            const uint64_t c = pass == 0 ? std::min<uint64_t>(chunks, 8) : chunks;
+            cudaEventRecord(e0, eng->s_copy);
+            for (uint64_t i = 0; i < c; ++i) {
+                char* h = slots[i % depth];
+                char* d = dev + (i % depth) * sb;
+                if (kind == TSNAP_PROBE_D2H) cudaMemcpyAsync(h, d, sb, cudaMemcpyDeviceToHost, eng->s_copy);
+                else cudaMemcpyAsync(d, h, sb, cudaMemcpyHostToDevice, eng->s_copy);
+            }
+            cudaEventRecord(e1, eng->s_copy);
+            cudaEventSynchronize(e1);
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        for (char* p : slots) eng->ring.release(p);
+        cudaFree(dev);
+        *out_gbs = ms > 0 ? double(chunks * sb) / 1e9 / (ms / 1e3) : 0;
+        return TSNAP_OK;
+    }
+    if (kind != TSNAP_PROBE_WRITE && kind != TSNAP_PROBE_READ) return set_err(TSNAP_EINVAL, "unknown probe kind");
+    if (!dir) return set_err(TSNAP_EINVAL, "null dir");
+    // same shape as a save job: files of 8 chunks, chunks of different files interleaved, I/O by the engine's workers
+    const bool save = kind == TSNAP_PROBE_WRITE;
+    const uint64_t per_file = 8;
+    const uint64_t nfiles = (chunks + per_file - 1) / per_file;
+    std::vector<int> fds(nfiles, -1);
+    std::string base = std::string(dir) + "/tsnap_probe_" + std::to_string(getpid()) + "_";
+    if (make_parent_dirs(base) != 0) return set_err(TSNAP_EIO, std::string("mkdir ") + dir + ": " + strerror(errno));
+    for (uint64_t i = 0; i < nfiles; ++i) {
+        const std::string path = base + std::to_string(i);
+        int flags = save ? (O_WRONLY | O_CREAT | O_TRUNC) : O_RDONLY;
+        if (eng->odirect) {
+            fds[i] = open(path.c_str(), flags | O_DIRECT, 0644);
+        }
+        if (fds[i] < 0) fds[i] = open(path.c_str(), flags, 0644);
+        if (fds[i] < 0) {
+            for (int fd : fds)
+                if (fd >= 0) close(fd);
+            return set_err(TSNAP_EIO, "open " + path + ": " + strerror(errno));
+        }
+    }
+    std::atomic<uint64_t> left{chunks};
+    std::atomic<int> err{0};
+    std::mutex mu;
+    std::condition_variable cv;
+    auto t0 = clk::now();
+    for (uint64_t c = 0; c < chunks; ++c) {
+        const uint64_t fi = c % nfiles, k = c / nfiles;
+        char* slot = eng->ring.acquire();
+        eng->io->post([&, fi, k, slot] {
+            int r = save ? pwrite_all(fds[fi], slot, sb, k * sb) : pread_all(fds[fi], slot, sb, k * sb);
+            if (r != 0) err.store(errno ? errno : EIO);
+            eng->ring.release(slot);
+            if (left.fetch_sub(1) == 1) {
+                std::lock_guard<std::mutex> g(mu);
+                cv.notify_all();
+            }
+        });
+    }
+    {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return left.load() == 0; });
+    }
+    const double ms = ms_since(t0);
+    for (int fd : fds) close(fd);
+    if (err.load()) return set_err(TSNAP_EIO, std::string("probe I/O failed: ") + strerror(err.load()));
+    *out_gbs = double(chunks * sb) / 1e9 / (ms / 1e3);
     return TSNAP_OK;
 }
 
@@ -1451,7 +1916,6 @@ int tsnap_buffer_release(tsnap_buffer* buf) {
 int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes, const tsnap_copy_desc* members,
                   int32_t n, void* consumer_stream) {
     if (!eng || (nbytes && !host_buf) || (n > 0 && !members)) return set_err(TSNAP_EINVAL, "null argument");
-    (void)consumer_stream;
     std::string err;
     // host destinations: plain host execution against the caller's buffer
     std::vector<tsnap_copy_desc> dev;
@@ -1482,7 +1946,7 @@ int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes, cons
         }
     }
     job->files[0].mem_src = static_cast<const char*>(host_buf);
-    rc = submit(job, nullptr, true);
+    rc = submit(job, consumer_stream, true);
     if (rc != TSNAP_OK) {
         delete job;
         return rc;

@@ -22,7 +22,8 @@ const char* last_err();
 
 class WorkerPool {
    public:
-    WorkerPool(int n, const std::vector<int>& cpus);
+    // cpus[i % cpus.size()] = CPU set worker i is bound to (empty vector / empty set = unbound)
+    WorkerPool(int n, const std::vector<std::vector<int>>& cpus);
     ~WorkerPool();
     void post(std::function<void()> fn);
     int size() const { return int(threads_.size()); }
@@ -39,15 +40,17 @@ class WorkerPool {
 // fixed-size pinned slots handed out to in-flight chunks
 class SlotRing {
    public:
-    int init(size_t slot_bytes, int n, bool pinned);
+    // every slot has `slack` extra bytes of capacity behind slot_bytes (O_DIRECT reads are widened to 4 KiB blocks)
+    int init(size_t slot_bytes, int n, bool pinned, size_t slack);
     void destroy();
     char* acquire();  // blocks
     void release(char* p);
     size_t slot_bytes() const { return slot_bytes_; }
-    size_t total_bytes() const { return slot_bytes_ * all_.size(); }
+    size_t total_bytes() const { return (slot_bytes_ + slack_) * all_.size(); }
+    int count() const { return int(all_.size()); }
 
    private:
-    size_t slot_bytes_ = 0;
+    size_t slot_bytes_ = 0, slack_ = 0;
     bool pinned_ = false;
     std::vector<char*> all_;
     std::vector<char*> free_;
@@ -65,6 +68,9 @@ struct tsnap_engine {
     int sm_count = 0;
     bool has_device = false;
     bool allow_bulk = true;
+    bool trace = false;      // TSNAP_ENGINE_TRACE
+    bool odirect = false;    // TSNAP_ENGINE_ODIRECT
+    bool no_arena = false;   // TSNAP_ENGINE_NO_ARENA
     std::vector<int> numa_cpus;  // CPUs of the NUMA node the GPU hangs off (empty = no binding)
     cudaStream_t s_kernel = nullptr;  // pack / unpack kernels
     cudaStream_t s_copy = nullptr;    // D2H / H2D payload copies
@@ -95,7 +101,7 @@ struct tsnap_engine {
     bool stopping = false;
     bool trim_arena = false;    // drain thread frees the HBM arena when it is idle
     bool busy = false;          // a job is being issued by the drain thread
-    bool release_arena_after_job = false;  // TSNAP_B200_RELEASE_ARENA=1
+    bool keep_arena = false;    // TSNAP_B200_KEEP_ARENA=1: do not give the engine-owned arena back when idle
     // event pool
     std::mutex ev_mu;
     std::vector<cudaEvent_t> ev_free;
@@ -114,14 +120,23 @@ struct FileSpec {
     uint64_t nbytes = 0;
     std::vector<tsnap_copy_desc> members;
     bool host_only = false;  // every member lives in HOST space
+    bool dense = false;      // every member is one dense, cast-free run: can be drained without staging
+    bool direct = false;     // chosen for this job: D2H straight from the live tensors (no arena, no pack)
+    struct Seg {             // dense runs of a dense file: wire offset, tensor-side address, length
+        uint64_t off, addr, bytes;
+    };
+    std::vector<Seg> segs;
     int fd = -1;
+    bool opened = false, open_failed = false, direct_io = false;
+    std::mutex open_mu;
     std::atomic<int64_t> parts_left{0};
     uint64_t arena_off = 0;  // offset inside the wave's arena region
     int wave = -1;
     const char* mem_src = nullptr;  // load: the "file" is caller memory (consumer seam)
     FileSpec() = default;
     FileSpec(const FileSpec& o)
-        : path(o.path), offset(o.offset), nbytes(o.nbytes), members(o.members), host_only(o.host_only), fd(o.fd),
+        : path(o.path), offset(o.offset), nbytes(o.nbytes), members(o.members), host_only(o.host_only), dense(o.dense),
+          direct(o.direct), segs(o.segs), fd(o.fd), opened(o.opened), open_failed(o.open_failed), direct_io(o.direct_io),
           arena_off(o.arena_off), wave(o.wave), mem_src(o.mem_src) {
         parts_left.store(o.parts_left.load());
     }
@@ -129,6 +144,7 @@ struct FileSpec {
 
 struct Wave {
     std::vector<int> files;
+    bool direct = false;      // pseudo-wave of direct files: no kernels, no arena region
     uint64_t bytes = 0;       // arena bytes (256B-aligned file regions)
     uint64_t region_off = 0;  // offset of the region inside the arena
     std::vector<Member> members;
@@ -136,6 +152,8 @@ struct Wave {
     void* d_tables = nullptr;
     size_t table_bytes = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr;  // kernel timing
+    bool timed = false;
+    double kernel_ms = 0;
     cudaEvent_t ev_done = nullptr;                                    // kernels finished
     cudaEvent_t ev_copied = nullptr;                                  // all payload copies of the wave finished
     std::atomic<int64_t> chunks_to_upload{0};                         // load: H2D chunks not yet issued
@@ -149,12 +167,24 @@ struct tsnap_job {
     tsnap_engine* eng = nullptr;
     int kind = tsnap::kSave;
     std::vector<tsnap::FileSpec> files;
-    std::deque<tsnap::Wave> waves;
+    std::deque<tsnap::Wave> waves;   // staged waves first, then at most one direct pseudo-wave
+    size_t n_staged_waves = 0;
     cudaEvent_t ev_producer = nullptr;
     cudaEvent_t ev_copy_begin = nullptr, ev_copy_end = nullptr;  // timing of the payload D2H span
     void* consumer_stream = nullptr;
     bool submitted = false;
     bool holds_arena = false;  // released in part_done when the job completes
+    // HBM staging of this job: lent by the caller (tsnap_job_set_arena) or the engine's own
+    char* arena = nullptr;
+    uint64_t arena_bytes = 0;
+    bool arena_set = false;   // caller supplied one (possibly of 0 bytes = arena-less)
+    cudaEvent_t ev_consumer = nullptr;  // load: recorded on the consumer stream at submit
+    // timeline (TSNAP_ENGINE_TRACE)
+    std::mutex trace_mu;
+    std::vector<tsnap_trace_rec> trace;
+    double last_copy_done_ms = 0;  // completion thread only
+    void add_trace(int kind, int lane, int file, double t0, double t1, uint64_t bytes);
+    double now_ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_submit).count(); }
     bool accounted = false;  // parts_left (incl. the drain thread's own token) has been set
     // completion state
     std::mutex mu;
@@ -170,7 +200,7 @@ struct tsnap_job {
     // stats
     tsnap_job_stats stats{};
     bool timing_collected = false;
-    std::atomic<int64_t> slot_wait_us{0}, io_busy_us{0}, io_queue_us{0};
+    std::atomic<int64_t> slot_wait_us{0}, io_busy_us{0}, io_queue_us{0}, n_memcpy{0};
     std::chrono::steady_clock::time_point t_submit;
 
     void fail(int code, const std::string& msg);
