@@ -184,6 +184,8 @@ typedef struct tsnap_job_stats {
     uint64_t n_waves;           /* arena waves                                               */
     uint64_t direct_bytes;      /* payload drained straight from the live tensors (no pack)  */
     uint64_t n_memcpy;          /* cudaMemcpyAsync calls issued for payload                  */
+    uint64_t bytes_bulk;        /* logical bytes moved by the bulk (TMA) kernel              */
+    uint64_t bytes_lsu;         /* logical bytes moved by the LSU kernel                     */
 } tsnap_job_stats;
 int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
 

@@ -117,6 +117,8 @@ class JobStats(C.Structure):
         ("n_waves", C.c_uint64),
         ("direct_bytes", C.c_uint64),
         ("n_memcpy", C.c_uint64),
+        ("bytes_bulk", C.c_uint64),
+        ("bytes_lsu", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -513,6 +515,9 @@ class Engine:
         self.device = device
         self.flags = flags
         self.hbm_staging_bytes = hbm_staging_bytes
+        self.io_threads = io_threads or 16
+        self.pinned_slots = pinned_slots or 32
+        self.pinned_slot_bytes = pinned_slot_bytes or (32 << 20)
         # TSNAP_B200_ENGINE_ARENA=1: staging is the engine's own cudaMalloc'ed arena (what a C caller gets) instead
         # of memory lent from PyTorch's allocator
         self.owns_arena = os.environ.get("TSNAP_B200_ENGINE_ARENA", "0") == "1"

@@ -399,6 +399,7 @@ static int plan_wave(tsnap_job* job, Wave& w) {
                 const uint32_t mi = uint32_t(w.members.size());
                 w.members.push_back(m);
                 std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : w.tiles_lsu;
+                (m.mode == kModeBulk ? job->stats.bytes_bulk : job->stats.bytes_lsu) += m.bytes;
                 for (uint64_t t = 0; t < nt; ++t) tv.push_back(Tile{mi, uint32_t(t)});
             }
         }

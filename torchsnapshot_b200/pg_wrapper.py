@@ -8,6 +8,14 @@ import torch
 import torch.distributed as dist
 
 
+# number of collectives issued through PGWrapper objects of this process (bench.py reports the per-take count)
+COLLECTIVE_COUNT = {"total": 0}
+
+
+def _count() -> None:
+    COLLECTIVE_COUNT["total"] += 1
+
+
 class PGWrapper:
     def __init__(self, pg: Optional[dist.ProcessGroup] = None) -> None:
         self.pg = pg if pg is not None else (dist.group.WORLD if dist.is_available() and dist.is_initialized() else None)
@@ -24,6 +32,7 @@ class PGWrapper:
 
     def barrier(self) -> None:
         if not self._alone():
+            _count()
             if dist.get_backend(self.pg) == "nccl":
                 dist.barrier(group=self.pg, device_ids=[torch.cuda.current_device()])
             else:
@@ -31,12 +40,14 @@ class PGWrapper:
 
     def broadcast_object_list(self, obj_list: List[Any], src: int = 0) -> None:
         if not self._alone():
+            _count()
             dist.broadcast_object_list(obj_list, src=dist.get_global_rank(self.pg, src), group=self.pg)
 
     def all_gather_object(self, obj_list: List[Any], obj: Any) -> None:
         if self._alone():
             obj_list[0] = obj
         else:
+            _count()
             dist.all_gather_object(obj_list, obj, group=self.pg)
 
     def scatter_object_list(self, output_list: List[Any], input_list: Optional[List[Any]], src: int = 0) -> None:
@@ -59,4 +70,5 @@ class PGWrapper:
             self.broadcast_object_list(payload, src=src)
             output_list[0] = payload[rank]
             return
+        _count()
         dist.scatter_object_list(output_list, input_list if rank == src else None, src=dist.get_global_rank(self.pg, src), group=self.pg)

@@ -113,6 +113,10 @@ class _NativeJobs:
     def stats(self) -> List[dict]:
         return [j.stats() for j in self.jobs.values()]
 
+    def traces(self) -> List[List[dict]]:
+        """Per-chunk timelines (only when the engine was created with ENGINE_TRACE)."""
+        return [j.trace() for j in self.jobs.values() if j.engine.flags & _native.ENGINE_TRACE]
+
     def destroy(self) -> None:
         for j in self.jobs.values():
             j.destroy()
@@ -138,6 +142,7 @@ class PendingIOWork:
             if self.native is not None:
                 await loop.run_in_executor(None, self.native.wait)
                 LAST_STATS["save"] = self.native.stats()
+                LAST_STATS["save_trace"] = self.native.traces()
         finally:
             if self.native is not None:
                 self.native.destroy()
@@ -310,6 +315,7 @@ async def execute_read_reqs(read_reqs: List[ReadReq], storage: StoragePlugin, me
         if native is not None:
             await loop.run_in_executor(None, native.wait)
             LAST_STATS["load"] = native.stats()
+            LAST_STATS["load_trace"] = native.traces()
     finally:
         if native is not None:
             native.destroy()
