@@ -14,18 +14,38 @@ from tests.cases import CASES, apply_knobs
 from tests.test_parity_cpu import _golden, assert_matches_golden
 from tests.util import snapshot_digest, wire_bytes
 
-HAVE_REF = os.path.isdir("/root/reference/torchsnapshot")
-pytestmark = pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the staged copy travels to the GPU box (oracle/make_ref.sh); the read-only tree only exists in the build container
+REF_PARENT = next((p for p in (os.path.join(ROOT, "oracle", "_ref"), "/root/reference") if os.path.isdir(os.path.join(p, "torchsnapshot"))), None)
+pytestmark = pytest.mark.skipif(REF_PARENT is None, reason="reference not staged (oracle/make_ref.sh) and /root/reference not present")
+
+
+def test_staged_reference_is_the_unmodified_tree():
+    """oracle/_ref must be a verbatim copy: every file's sha256 equals the one recorded at staging time and, where the
+    read-only tree is present, the one of the file there."""
+    import hashlib
+
+    staged = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(staged, "torchsnapshot")):
+        pytest.skip("not staged")
+    want = dict(reversed(ln.split(None, 1)) for ln in open(os.path.join(staged, "MANIFEST.sha256")).read().splitlines() if ln.strip())
+    assert len(want) > 40
+    for rel, digest in want.items():
+        rel = rel.strip()
+        assert hashlib.sha256(open(os.path.join(staged, "torchsnapshot", rel), "rb").read()).hexdigest() == digest, rel
+        src = os.path.join("/root/reference/torchsnapshot", rel)
+        if os.path.isdir("/root/reference/torchsnapshot"):
+            assert hashlib.sha256(open(src, "rb").read()).hexdigest() == digest, rel
 
 
 @pytest.fixture()
 def ref():
-    sys.path.insert(0, "/root/reference")
+    sys.path.insert(0, REF_PARENT)
     os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
     try:
         import torchsnapshot
     finally:
-        sys.path.remove("/root/reference")
+        sys.path.remove(REF_PARENT)
     import torchsnapshot_b200 as B
 
     B.install(torchsnapshot)
