@@ -186,6 +186,9 @@ typedef struct tsnap_job_stats {
     uint64_t n_memcpy;          /* cudaMemcpyAsync calls issued for payload                  */
     uint64_t bytes_bulk;        /* logical bytes moved by the bulk (TMA) kernel              */
     uint64_t bytes_lsu;         /* logical bytes moved by the LSU kernel                     */
+    uint64_t bytes_rows;        /* logical bytes moved run by run by the rows (TMA) kernel   */
+    uint64_t n_tiles_rows;
+    double kernel_rows_ms;
 } tsnap_job_stats;
 int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
 
@@ -232,8 +235,8 @@ int tsnap_job_get_trace(tsnap_job* job, tsnap_trace_rec* out, uint64_t cap, uint
 /* ---- roofline probes: the engine's own link and sink, measured with its own ring and workers -----
  * D2H/H2D: `bytes` moved in ring-slot-sized cudaMemcpyAsync chunks between a scratch HBM buffer and
  * the pinned ring.  WRITE: `bytes` written from the ring to fresh files under `dir` by the I/O workers
- * (same chunking/interleaving as a save job, no D2H); READ reads those files back into the ring.
- * The caller removes `dir`.  out_gbs: bytes / 1e9 / seconds. */
+ * (same chunking/interleaving as a save job, no D2H); READ writes such files (untimed) and times reading
+ * them back into the ring.  Only the I/O is timed; the probe removes its files.  out_gbs: bytes/1e9/seconds. */
 enum tsnap_probe_kind { TSNAP_PROBE_D2H = 0, TSNAP_PROBE_H2D = 1, TSNAP_PROBE_WRITE = 2, TSNAP_PROBE_READ = 3 };
 int tsnap_engine_probe(tsnap_engine* eng, int kind, const char* dir, uint64_t bytes, double* out_gbs);
 
@@ -273,6 +276,7 @@ typedef struct tsnap_plan_info {
     uint64_t n_members_bulk, n_members_lsu, n_members_host;
     uint64_t n_tiles_bulk, n_tiles_lsu;
     uint64_t bytes_bulk, bytes_lsu, bytes_host;
+    uint64_t n_members_rows, n_tiles_rows, bytes_rows;
 } tsnap_plan_info;
 int tsnap_plan_describe(const tsnap_copy_desc* members, int32_t n_members, uint64_t wire_base_align,
                         tsnap_plan_info* out);

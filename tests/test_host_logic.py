@@ -122,3 +122,44 @@ def test_knobs_follow_the_reference_environment_variables(monkeypatch):
     from torchsnapshot_b200.scheduler import get_process_memory_budget_bytes
 
     assert get_process_memory_budget_bytes(PGWrapper(None)) == 4096
+
+
+def test_views_with_more_than_eight_dims(tmp_path):
+    """Descriptors hold 8 dims; views with more are folded (size-1 dims dropped, dense neighbours merged) and only a
+    view that still needs more than 8 strided dims is made contiguous first, like the reference does for every
+    non-contiguous source (T:batcher.py:156, T:serialization.py:196)."""
+    import torch
+
+    import torchsnapshot_b200 as B
+    from tests.util import wire_bytes
+
+    t = torch.randn(2, 3, 1, 2, 2, 3, 2, 2, 2, 2)  # 10-D contiguous
+    u = torch.randn(2, 3, 2, 2, 2, 3, 2, 2, 2, 4)[..., ::2]  # 10-D, last dim stepped: merges to 2 dims
+    v = torch.randn(3, 2, 2, 2, 2, 2, 2, 2, 2, 2).permute(9, 8, 7, 6, 5, 4, 3, 2, 1, 0)  # 10 non-mergeable dims
+    snap = B.Snapshot.take(str(tmp_path / "s"), {"m": B.StateDict(t=t, u=u, v=v)})
+    o = B.StateDict(t=torch.zeros_like(t), u=torch.zeros(2, 3, 2, 2, 2, 3, 2, 2, 2, 4)[..., ::2], v=torch.zeros(v.shape))
+    snap.restore({"m": o})
+    for k, a in (("t", t), ("u", u), ("v", v)):
+        assert wire_bytes(a) == wire_bytes(o[k]), k
+
+
+def test_cast_on_save_is_fused_and_matches_torch(tmp_path):
+    """cast_on_save: the entry promises the target dtype and the payload is exactly tensor.to(dtype) — without the
+    processed tensor ever being materialised (descriptor with dst_dtype != src_dtype; here executed by the host planner)."""
+    import torch
+
+    import torchsnapshot_b200 as B
+    from tests.util import wire_bytes
+
+    st = {"w": torch.randn(1000, 33), "wt": torch.randn(64, 48).t(), "i": torch.arange(10), "h": torch.randn(7).half(), "d": torch.randn(5, dtype=torch.float64)}
+    snap = B.Snapshot.take(str(tmp_path / "s"), {"m": B.StateDict(**st)}, _custom_tensor_prepare_func=B.cast_on_save(torch.bfloat16, only="m/w*"))
+    man = snap.get_manifest()
+    assert man["0/m/w"].dtype == "torch.bfloat16" and man["0/m/wt"].dtype == "torch.bfloat16"
+    assert man["0/m/h"].dtype == "torch.float16" and man["0/m/i"].dtype == "torch.int64" and man["0/m/d"].dtype == "torch.float64"
+    for k in ("w", "wt"):
+        data = open(tmp_path / "s" / man[f"0/m/{k}"].location, "rb").read()
+        assert data == wire_bytes(st[k].to(torch.bfloat16)), k
+    tgt = B.StateDict(w=torch.zeros(1000, 33, dtype=torch.bfloat16), wt=torch.zeros(48, 64, dtype=torch.bfloat16), i=torch.zeros(10, dtype=torch.long),
+                      h=torch.zeros(7).half(), d=torch.zeros(5, dtype=torch.float64))
+    snap.restore({"m": tgt})
+    assert torch.equal(tgt["w"], st["w"].bfloat16()) and torch.equal(tgt["wt"], st["wt"].bfloat16()) and torch.equal(tgt["d"], st["d"])

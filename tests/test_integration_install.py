@@ -80,3 +80,41 @@ def test_reference_api_runs_on_the_engine(ref, name, tmp_path):
             assert wire_bytes(a[k]) == wire_bytes(b[k]), k
         else:
             assert a[k] == b[k], k
+
+
+def test_storage_plugins_entry_point(ref, tmp_path, monkeypatch):
+    """pyproject.toml registers b200fs in the reference's `storage_plugins` entry-point group
+    (T:storage_plugin.py:56-67); resolve it the way the reference does and take/restore through it."""
+    import importlib
+    import tomllib
+
+    import torchsnapshot_b200 as B
+
+    B.uninstall()
+    proj = tomllib.load(open(os.path.join(ROOT, "pyproject.toml"), "rb"))
+    target = proj["project"]["entry-points"]["storage_plugins"]["b200fs"]
+    mod, attr = target.split(":")
+    factory = getattr(importlib.import_module(mod), attr)
+
+    class EP:  # what importlib.metadata hands the reference after `pip install`
+        name, value = "b200fs", target
+
+        @staticmethod
+        def load():
+            return factory
+
+    sp = importlib.import_module(ref.__name__ + ".storage_plugin")
+    monkeypatch.setattr(sp, "entry_points", lambda group=None: [EP] if group == "storage_plugins" else [])
+    build, knobs = CASES["slabs"]
+    state = build("cpu")
+    eng = B.get_engine(-1)
+    w0 = eng.stats()["bytes_written"]
+    with apply_knobs(knobs):
+        snap = ref.Snapshot.take("b200fs://" + str(tmp_path / "snap"), {"state": ref.StateDict(**state)})
+        assert eng.stats()["bytes_written"] > w0, "the engine was not put underneath the reference"
+        assert_matches_golden(snapshot_digest(str(tmp_path / "snap")), _golden("slabs"))
+        tgt = ref.StateDict(**{k: torch.zeros_like(v) if isinstance(v, torch.Tensor) else v for k, v in state.items()})
+        snap.restore({"state": tgt})
+    for k, v in state.items():
+        if isinstance(v, torch.Tensor):
+            assert wire_bytes(v) == wire_bytes(tgt[k]), k

@@ -152,3 +152,32 @@ def test_two_rank_manifest_equals_reference(tmp_path):
             sa[k]["byte_range"] = sb[k]["byte_range"] = None
         assert sa[k] == sb[k], k
     assert sum(v.get("nbytes", 0) for v in a["files"].values()) == sum(v.get("nbytes", 0) for v in b["files"].values())
+
+
+def _subgroup_worker(rank: int, world: int, store_path: str, root: str):
+    """Ranks that took a different number of async snapshots (a take on a sub-group, then one on WORLD) must still
+    agree on the commit rendezvous of the WORLD take (it used to be tagged by a process-global counter)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)
+    import torchsnapshot_b200 as M
+
+    sub = dist.new_group([0, 1])
+    t = det_tensor((50, 7), torch.float32, rank)
+    if rank in (0, 1):
+        M.Snapshot.async_take(os.path.join(root, "sub"), {"s": M.StateDict(t=t)}, pg=sub).wait()
+        assert os.path.exists(os.path.join(root, "sub", ".snapshot_metadata"))
+    snap = M.Snapshot.async_take(os.path.join(root, "world"), {"s": M.StateDict(t=t)}).wait()
+    dist.barrier()
+    out = M.StateDict(t=torch.zeros(50, 7))
+    snap.restore({"s": out})
+    assert wire_bytes(out["t"]) == wire_bytes(t)
+    # a second take on the same groups keeps working (keys of the first were cleared, tags advance per group)
+    M.Snapshot.async_take(os.path.join(root, "world2"), {"s": M.StateDict(t=t)}).wait()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_async_commit_tags_are_per_process_group(tmp_path):
+    store = tempfile.NamedTemporaryFile(delete=False)
+    mp.spawn(_subgroup_worker, args=(3, store.name, str(tmp_path)), nprocs=3, join=True)
+    assert os.path.exists(tmp_path / "world" / ".snapshot_metadata") and os.path.exists(tmp_path / "world2" / ".snapshot_metadata")

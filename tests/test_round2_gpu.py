@@ -117,6 +117,14 @@ def test_c3_rank_shard_matches_oracle_at_full_size(tmp_path, pg):
     _assert_snapshot_equals_oracle(str(tmp_path / "s"), entries, files)
 
 
+def _device_job_stats():
+    """Stats of the engine job that touched the GPU (a mixed CPU/GPU state also has a host-only job for the CPU tensors)."""
+    from torchsnapshot_b200 import scheduler as S
+
+    jobs = S.LAST_STATS.get("save") or [{}]
+    return max(jobs, key=lambda j: (j.get("n_kernel_launches", 0), j.get("direct_bytes", 0), j.get("payload_bytes", 0)))
+
+
 def _c2_flat(app_state):
     flat = {}
     for key in ("model", "optim"):
@@ -131,9 +139,7 @@ def test_c2_layout_matches_oracle(tmp_path, pg):
     app_state, kw, payload = W.build_c2(B, 0, 1, torch.device(DEV), 0)
     k0 = B.get_engine(0).stats()["kernels_launched"]
     B.Snapshot.take(str(tmp_path / "s"), app_state)  # per-rank state: request order == state_dict order (oracle models this)
-    from torchsnapshot_b200 import scheduler as S
-
-    st = (S.LAST_STATS.get("save") or [{}])[0]
+    st = _device_job_stats()
     flat = _c2_flat(app_state)
     entries, files = R.plan_save(flat)
     assert sum(len(b) for b in files.values()) == payload
@@ -209,11 +215,10 @@ def test_install_under_unmodified_reference_with_cuda_tensors(ref, tmp_path, pg)
 # ---- HBM staging: arena-less, bounded, engine-owned, nearly full device ----------------------------------------------
 def _save_and_check(tmp_path, tag, state, expect=None):
     snap = B.Snapshot.take(str(tmp_path / tag), {"m": B.StateDict(**state)})
-    from torchsnapshot_b200 import scheduler as S
-
-    st = (S.LAST_STATS.get("save") or [{}])[0]
+    st = _device_job_stats()
     flat = {k: v for k, v in flatten(state, "m")[1].items() if isinstance(v, torch.Tensor)}
-    entries, files = R.plan_save(flat)
+    slab = int(os.environ.get("TORCHSNAPSHOT_SLAB_SIZE_THRESHOLD_BYTES_OVERRIDE", R.DEFAULT_SLAB_THRESHOLD))
+    entries, files = R.plan_save(flat, slab_threshold=slab)
     _assert_snapshot_equals_oracle(str(tmp_path / tag), entries, files)
     tgt = B.StateDict(**{k: torch.zeros_like(v) for k, v in state.items()})
     snap.restore({"m": tgt})

@@ -1,0 +1,103 @@
+"""The copy-engine rows kernel (strided members with long 16 B-aligned runs: column shards, narrow on dim != 0,
+reshard boxes) and the shared-memory tiled transpose, both directions, against the oracle's serialization."""
+import pytest
+import torch
+
+from oracle import ref_port as R
+from tests.util import det_tensor
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pack(eng, views, offs, total):
+    from torchsnapshot_b200 import _native as N
+
+    descs = [N.save_desc(v, o) for v, o in zip(views, offs)]
+    sb = eng.stage(descs, total, stream=torch.cuda.current_stream().cuda_stream, keepalive=views)
+    got = bytes(sb.wait())
+    st = sb.stats()
+    sb.release()
+    return got, st
+
+
+def _roundtrip(views, expect_mode):
+    """pack the views back to back (16 B-aligned offsets), compare with the oracle, scatter into same-strided twins."""
+    from torchsnapshot_b200 import _native as N
+
+    eng = N.get_engine(0)
+    offs, off, want = [], 0, []
+    for v in views:
+        offs.append(off)
+        b = R.serialize_view(v)
+        want.append(b)
+        off += (len(b) + 15) // 16 * 16
+    got, st = _pack(eng, views, offs, off)
+    for i, (o, b) in enumerate(zip(offs, want)):
+        assert got[o : o + len(b)] == b, (i, tuple(views[i].shape), views[i].stride(), views[i].dtype)
+    expect_mode(st)
+    dests = []
+    for v in views:
+        d = torch.empty_strided(v.shape, v.stride(), dtype=v.dtype, device=DEV)
+        d.zero_()
+        dests.append(d)
+    eng.consume(got, [N.load_desc(d, o) for d, o in zip(dests, offs)])
+    for i, (d, b) in enumerate(zip(dests, want)):
+        assert R.serialize_view(d) == b, ("scatter", i)
+    return st
+
+
+def test_rows_kernel_column_shards_and_boxes():
+    base = det_tensor((4096, 1024), torch.float32, 1).to(DEV)      # 4 KiB rows
+    wide = det_tensor((300, 40000), torch.bfloat16, 2).to(DEV)     # 80 KB rows: runs longer than a 48 KiB stage
+    cube = det_tensor((6, 50, 640), torch.float32, 3).to(DEV)
+    views = [
+        base[:, 128:256],          # 512 B runs in 4 KiB-pitched rows (torchrec COLUMN_WISE shard)
+        base[100:3000, 512:],      # 2 KiB runs, row offset
+        wide[:, 8:32776],          # 65 536 B runs (> stage size), 16 B-aligned start
+        cube[1:5, :, 64:320],      # two outer dims, 1 KiB runs
+        base[::2, 256:512],        # stepped rows
+    ]
+
+    def rows(st):
+        assert st["n_tiles_rows"] > 0 and st["bytes_rows"] == sum(v.numel() * v.element_size() for v in views), st
+
+    _roundtrip(views, rows)
+
+
+def test_rows_kernel_declines_short_or_unaligned_runs():
+    base = det_tensor((2048, 256), torch.float32, 4).to(DEV)
+    views = [base[:, 4:36], base[:, 1:129]]  # 128 B runs (too short); 512 B runs starting 4 B off 16 B alignment
+
+    def lsu(st):
+        assert st["n_tiles_rows"] == 0 and st["n_tiles_lsu"] > 0
+
+    _roundtrip(views, lsu)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64, torch.uint8, torch.int64])
+def test_tiled_transpose(dtype):
+    a = det_tensor((300, 200), dtype, 5).to(DEV)
+    b = det_tensor((1000, 1037), dtype, 6).to(DEV)
+    c = det_tensor((5, 130, 70), dtype, 7).to(DEV)
+    views = [a.t(), b.t(), c.permute(0, 2, 1), c.permute(2, 0, 1), b.t()[3:900, 10:1000], c.transpose(0, 2)]
+
+    def any_mode(st):
+        assert st["n_tiles_lsu"] > 0
+
+    _roundtrip(views, any_mode)
+
+
+def test_transpose_and_rows_through_snapshot_api(tmp_path):
+    import torchsnapshot_b200 as B
+    from tests.util import wire_bytes
+
+    w = det_tensor((2048, 3072), torch.bfloat16, 8).to(DEV)
+    state = {"wt": w.t(), "cols": w[:, 1024:2048], "dense": w}
+    snap = B.Snapshot.take(str(tmp_path / "s"), {"m": B.StateDict(**state)})
+    tgt = {"wt": torch.zeros(3072, 2048, dtype=torch.bfloat16, device=DEV), "cols": torch.zeros(2048, 3072, dtype=torch.bfloat16, device=DEV)[:, 5:1029],
+           "dense": torch.zeros_like(w)}
+    sd = B.StateDict(**tgt)
+    snap.restore({"m": sd})
+    for k in state:
+        assert wire_bytes(state[k]) == wire_bytes(sd[k]), k

@@ -119,6 +119,9 @@ class JobStats(C.Structure):
         ("n_memcpy", C.c_uint64),
         ("bytes_bulk", C.c_uint64),
         ("bytes_lsu", C.c_uint64),
+        ("bytes_rows", C.c_uint64),
+        ("n_tiles_rows", C.c_uint64),
+        ("kernel_rows_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -156,6 +159,9 @@ class PlanInfo(C.Structure):
         ("bytes_bulk", C.c_uint64),
         ("bytes_lsu", C.c_uint64),
         ("bytes_host", C.c_uint64),
+        ("n_members_rows", C.c_uint64),
+        ("n_tiles_rows", C.c_uint64),
+        ("bytes_rows", C.c_uint64),
     ]
 
 
@@ -269,19 +275,56 @@ def _space_of(t: torch.Tensor) -> int:
     raise NativeError(-6, f"tensors on {t.device} are not supported")
 
 
-def _fill_view(d: CopyDesc, t: torch.Tensor) -> None:
-    if t.dim() > MAX_DIMS:
-        raise NativeError(-6, f"tensors with more than {MAX_DIMS} dims are not supported")
-    d.ndim = t.dim()
-    for i, s in enumerate(t.shape):
-        d.sizes[i] = s
+def _merge_dims(sizes: Sequence[int], *stride_sets: Sequence[int]):
+    """Folds size-1 dims away and merges neighbours that are dense across their boundary on EVERY side (what the native
+    planner does as well); used to fit views of more than MAX_DIMS dims into a descriptor."""
+    out_sizes: List[int] = []
+    out_strides: List[List[int]] = [[] for _ in stride_sets]
+    for i, n in enumerate(sizes):
+        if n == 1:
+            continue
+        st = [ss[i] for ss in stride_sets]
+        if out_sizes and all(o[-1] == s_i * n for o, s_i in zip(out_strides, st)):
+            out_sizes[-1] *= n
+            for o, s_i in zip(out_strides, st):
+                o[-1] = s_i
+        else:
+            out_sizes.append(n)
+            for o, s_i in zip(out_strides, st):
+                o.append(s_i)
+    return out_sizes, out_strides
+
+
+def _c_strides(shape: Sequence[int]) -> List[int]:
+    acc, out = 1, [0] * len(shape)
+    for i in range(len(shape) - 1, -1, -1):
+        out[i] = acc
+        acc *= shape[i]
+    return out
+
+
+def needs_contiguous_copy(t: torch.Tensor) -> bool:
+    """True for the (exotic) views that still need more than MAX_DIMS strided dims after folding: the caller makes
+    them contiguous first — what the reference does for every non-contiguous source (T:batcher.py:156) — and keeps
+    that copy alive for the duration of the job."""
+    if t.dim() <= MAX_DIMS:
+        return False
+    sizes, _ = _merge_dims(list(t.shape), list(t.stride()), _c_strides(list(t.shape)))
+    return len(sizes) > MAX_DIMS
 
 
 def save_desc(t: torch.Tensor, wire_offset: int, wire_dtype: Optional[torch.dtype] = None) -> CopyDesc:
     """tensor view -> wire image at ``wire_offset`` (C-contiguous layout of ``t.shape``)."""
     d = CopyDesc()
-    _fill_view(d, t)
-    for i, s in enumerate(t.stride()):
+    sizes, strides = list(t.shape), list(t.stride())
+    if len(sizes) > MAX_DIMS:
+        # the wire side is C-contiguous: it merges wherever the source does
+        sizes, (strides, _) = _merge_dims(sizes, strides, _c_strides(sizes))
+        if len(sizes) > MAX_DIMS:
+            raise NativeError(-6, f"view does not reduce to {MAX_DIMS} strided dims (see needs_contiguous_copy)")
+    d.ndim = len(sizes)
+    for i, (n, s) in enumerate(zip(sizes, strides)):
+        d.sizes[i] = n
         d.src_strides[i] = s
     d.src_addr = t.data_ptr()
     d.dst_addr = wire_offset
@@ -301,18 +344,17 @@ def load_desc(
     """wire bytes at ``wire_offset`` -> tensor view.  ``wire_strides`` (elements) describe the saved
     piece when ``t`` receives a sub-box of it (reshard-on-load); default: the piece has ``t``'s shape."""
     d = CopyDesc()
-    _fill_view(d, t)
-    if wire_strides is None:
-        acc = 1
-        ws = [0] * t.dim()
-        for i in range(t.dim() - 1, -1, -1):
-            ws[i] = acc
-            acc *= t.shape[i]
-        wire_strides = ws
-    for i, s in enumerate(wire_strides):
-        d.src_strides[i] = s
-    for i, s in enumerate(t.stride()):
-        d.dst_strides[i] = s
+    sizes, dstrides = list(t.shape), list(t.stride())
+    wstrides = list(wire_strides) if wire_strides is not None else _c_strides(sizes)
+    if len(sizes) > MAX_DIMS:
+        sizes, (wstrides, dstrides) = _merge_dims(sizes, wstrides, dstrides)
+        if len(sizes) > MAX_DIMS:
+            raise NativeError(-6, f"destination view does not reduce to {MAX_DIMS} strided dims")
+    d.ndim = len(sizes)
+    for i, (n, ws, ds) in enumerate(zip(sizes, wstrides, dstrides)):
+        d.sizes[i] = n
+        d.src_strides[i] = ws
+        d.dst_strides[i] = ds
     d.src_addr = wire_offset
     d.dst_addr = t.data_ptr()
     d.src_dtype = tsnap_dtype(wire_dtype or t.dtype)

@@ -398,13 +398,14 @@ static int plan_wave(tsnap_job* job, Wave& w) {
                 if (nt == 0) continue;
                 const uint32_t mi = uint32_t(w.members.size());
                 w.members.push_back(m);
-                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : w.tiles_lsu;
-                (m.mode == kModeBulk ? job->stats.bytes_bulk : job->stats.bytes_lsu) += m.bytes;
+                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : w.tiles_lsu;
+                (m.mode == kModeBulk ? job->stats.bytes_bulk : m.mode == kModeRows ? job->stats.bytes_rows : job->stats.bytes_lsu) += m.bytes;
                 for (uint64_t t = 0; t < nt; ++t) tv.push_back(Tile{mi, uint32_t(t)});
             }
         }
     }
     job->stats.n_tiles_bulk += w.tiles_bulk.size();
+    job->stats.n_tiles_rows += w.tiles_rows.size();
     job->stats.n_tiles_lsu += w.tiles_lsu.size();
     return TSNAP_OK;
 }
@@ -414,15 +415,18 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     tsnap_engine* eng = job->eng;
     const size_t mb = w.members.size() * sizeof(Member);
     const size_t bb = w.tiles_bulk.size() * sizeof(Tile);
+    const size_t rb = w.tiles_rows.size() * sizeof(Tile);
     const size_t lb = w.tiles_lsu.size() * sizeof(Tile);
-    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(lb, 256);
+    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256);
     CUDA_TRY(cudaEventCreate(&w.ev_k0));
     CUDA_TRY(cudaEventCreate(&w.ev_k1));
+    CUDA_TRY(cudaEventCreate(&w.ev_kr));
     CUDA_TRY(cudaEventCreate(&w.ev_k2));
     CUDA_TRY(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
     if (w.members.empty()) {
         CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
         CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
+        CUDA_TRY(cudaEventRecord(w.ev_kr, eng->s_kernel));
         CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
         CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
         return TSNAP_OK;
@@ -431,35 +435,41 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     char* d = static_cast<char*>(w.d_tables);
     Member* d_members = reinterpret_cast<Member*>(d);
     Tile* d_bulk = reinterpret_cast<Tile*>(d + align_up(mb, 256));
-    Tile* d_lsu = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256));
+    Tile* d_rows = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256));
+    Tile* d_lsu = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256));
     // pageable sources: the runtime stages them before returning, so the vectors may be freed later
     CUDA_TRY(cudaMemcpyAsync(d_members, w.members.data(), mb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (bb) CUDA_TRY(cudaMemcpyAsync(d_bulk, w.tiles_bulk.data(), bb, cudaMemcpyHostToDevice, eng->s_kernel));
+    if (rb) CUDA_TRY(cudaMemcpyAsync(d_rows, w.tiles_rows.data(), rb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (lb) CUDA_TRY(cudaMemcpyAsync(d_lsu, w.tiles_lsu.data(), lb, cudaMemcpyHostToDevice, eng->s_kernel));
-    job->stats.table_h2d_bytes += mb + bb + lb;
+    job->stats.table_h2d_bytes += mb + bb + rb + lb;
     CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
     CUDA_TRY(launch_bulk(d_members, d_bulk, uint32_t(w.tiles_bulk.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
+    CUDA_TRY(launch_rows(d_members, d_rows, uint32_t(w.tiles_rows.size()), eng->sm_count, eng->s_kernel));
+    CUDA_TRY(cudaEventRecord(w.ev_kr, eng->s_kernel));
     CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
     CUDA_TRY(cudaFreeAsync(w.d_tables, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
-    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1);
+    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1);
     job->stats.n_kernel_launches += nl;
     eng->kernels_launched += nl;
     return TSNAP_OK;
 }
 
 static void collect_wave_timing(tsnap_job* job, Wave& w) {
-    float a = 0, b = 0;
+    float a = 0, r = 0, b = 0;
     if (w.timed || !w.ev_k0) return;
-    if (cudaEventElapsedTime(&a, w.ev_k0, w.ev_k1) == cudaSuccess && cudaEventElapsedTime(&b, w.ev_k1, w.ev_k2) == cudaSuccess) {
+    if (cudaEventElapsedTime(&a, w.ev_k0, w.ev_k1) == cudaSuccess && cudaEventElapsedTime(&r, w.ev_k1, w.ev_kr) == cudaSuccess &&
+        cudaEventElapsedTime(&b, w.ev_kr, w.ev_k2) == cudaSuccess) {
         std::lock_guard<std::mutex> g(job->mu);
         w.timed = true;
         job->stats.kernel_bulk_ms += a;
+        job->stats.kernel_rows_ms += r;
         job->stats.kernel_lsu_ms += b;
-        job->stats.kernel_ms += a + b;
-        w.kernel_ms = a + b;
+        job->stats.kernel_ms += a + r + b;
+        w.kernel_ms = a + r + b;
     }
 }
 
@@ -1046,9 +1056,11 @@ static int run_load_inner(tsnap_job* job) {
     // the scatter kernels (s_kernel) and, for files uploaded straight into the live tensors, the copies (s_copy).
     bool any_direct = false;
     for (Wave& w : job->waves) any_direct = any_direct || w.direct;
+    // A lent arena comes from the caller's stream-ordered allocator: the block may still be in use by kernels queued
+    // on that stream (its previous owner was freed "in stream order"), so uploads into it wait as well.
     if (job->ev_consumer) {
         if (job->n_staged_waves) cudaStreamWaitEvent(eng->s_kernel, job->ev_consumer, 0);
-        if (any_direct) cudaStreamWaitEvent(eng->s_copy, job->ev_consumer, 0);
+        if (any_direct || (job->arena_set && job->n_staged_waves)) cudaStreamWaitEvent(eng->s_copy, job->ev_consumer, 0);
     }
 
     auto shared = std::make_shared<LoadShared>();
@@ -1663,6 +1675,7 @@ int tsnap_job_destroy(tsnap_job* job) {
     for (Wave& w : job->waves) {
         if (w.ev_k0) cudaEventDestroy(w.ev_k0);
         if (w.ev_k1) cudaEventDestroy(w.ev_k1);
+        if (w.ev_kr) cudaEventDestroy(w.ev_kr);
         if (w.ev_k2) cudaEventDestroy(w.ev_k2);
         if (w.ev_done) cudaEventDestroy(w.ev_done);
         if (w.ev_copied) cudaEventDestroy(w.ev_copied);
@@ -1762,50 +1775,59 @@ int tsnap_engine_probe(tsnap_engine* eng, int kind, const char* dir, uint64_t by
     }
     if (kind != TSNAP_PROBE_WRITE && kind != TSNAP_PROBE_READ) return set_err(TSNAP_EINVAL, "unknown probe kind");
     if (!dir) return set_err(TSNAP_EINVAL, "null dir");
-    // same shape as a save job: files of 8 chunks, chunks of different files interleaved, I/O by the engine's workers
-    const bool save = kind == TSNAP_PROBE_WRITE;
+    // Same shape as a save job: files of 8 chunks, chunks of different files interleaved, I/O by the engine's workers.
+    // Every call uses fresh file names (writes never truncate an older probe's dirty pages) and removes its files; the
+    // READ probe first writes its files (untimed), then times reading them back.  Only the I/O itself is timed.
+    static std::atomic<uint64_t> serial{0};
     const uint64_t per_file = 8;
     const uint64_t nfiles = (chunks + per_file - 1) / per_file;
     std::vector<int> fds(nfiles, -1);
-    std::string base = std::string(dir) + "/tsnap_probe_" + std::to_string(getpid()) + "_";
+    std::vector<std::string> paths(nfiles);
+    std::string base = std::string(dir) + "/tsnap_probe_" + std::to_string(getpid()) + "_" + std::to_string(serial.fetch_add(1)) + "_";
     if (make_parent_dirs(base) != 0) return set_err(TSNAP_EIO, std::string("mkdir ") + dir + ": " + strerror(errno));
+    auto cleanup = [&] {
+        for (size_t i = 0; i < fds.size(); ++i) {
+            if (fds[i] >= 0) close(fds[i]);
+            if (!paths[i].empty()) unlink(paths[i].c_str());
+        }
+    };
     for (uint64_t i = 0; i < nfiles; ++i) {
-        const std::string path = base + std::to_string(i);
-        int flags = save ? (O_WRONLY | O_CREAT | O_TRUNC) : O_RDONLY;
-        if (eng->odirect) {
-            fds[i] = open(path.c_str(), flags | O_DIRECT, 0644);
-        }
-        if (fds[i] < 0) fds[i] = open(path.c_str(), flags, 0644);
+        paths[i] = base + std::to_string(i);
+        const int flags = O_RDWR | O_CREAT | O_TRUNC;
+        if (eng->odirect) fds[i] = open(paths[i].c_str(), flags | O_DIRECT, 0644);
+        if (fds[i] < 0) fds[i] = open(paths[i].c_str(), flags, 0644);
         if (fds[i] < 0) {
-            for (int fd : fds)
-                if (fd >= 0) close(fd);
-            return set_err(TSNAP_EIO, "open " + path + ": " + strerror(errno));
+            const std::string msg = "open " + paths[i] + ": " + strerror(errno);
+            cleanup();
+            return set_err(TSNAP_EIO, msg);
         }
     }
-    std::atomic<uint64_t> left{chunks};
     std::atomic<int> err{0};
-    std::mutex mu;
-    std::condition_variable cv;
-    auto t0 = clk::now();
-    for (uint64_t c = 0; c < chunks; ++c) {
-        const uint64_t fi = c % nfiles, k = c / nfiles;
-        char* slot = eng->ring.acquire();
-        eng->io->post([&, fi, k, slot] {
-            int r = save ? pwrite_all(fds[fi], slot, sb, k * sb) : pread_all(fds[fi], slot, sb, k * sb);
-            if (r != 0) err.store(errno ? errno : EIO);
-            eng->ring.release(slot);
-            if (left.fetch_sub(1) == 1) {
-                std::lock_guard<std::mutex> g(mu);
-                cv.notify_all();
-            }
-        });
-    }
-    {
+    auto pass = [&](bool write) -> double {
+        std::atomic<uint64_t> left{chunks};
+        std::mutex mu;
+        std::condition_variable cv;
+        auto t0 = clk::now();
+        for (uint64_t c = 0; c < chunks; ++c) {
+            const uint64_t fi = c % nfiles, k = c / nfiles;
+            char* slot = eng->ring.acquire();
+            eng->io->post([&, fi, k, slot, write] {
+                int r = write ? pwrite_all(fds[fi], slot, sb, k * sb) : pread_all(fds[fi], slot, sb, k * sb);
+                if (r != 0) err.store(errno ? errno : EIO);
+                eng->ring.release(slot);
+                if (left.fetch_sub(1) == 1) {
+                    std::lock_guard<std::mutex> g(mu);
+                    cv.notify_all();
+                }
+            });
+        }
         std::unique_lock<std::mutex> g(mu);
         cv.wait(g, [&] { return left.load() == 0; });
-    }
-    const double ms = ms_since(t0);
-    for (int fd : fds) close(fd);
+        return ms_since(t0);
+    };
+    double ms = pass(true);
+    if (kind == TSNAP_PROBE_READ && !err.load()) ms = pass(false);
+    cleanup();
     if (err.load()) return set_err(TSNAP_EIO, std::string("probe I/O failed: ") + strerror(err.load()));
     *out_gbs = double(chunks * sb) / 1e9 / (ms / 1e3);
     return TSNAP_OK;
@@ -1974,18 +1996,22 @@ int tsnap_plan_describe(const tsnap_copy_desc* members, int32_t n, uint64_t wire
         for (int k = 0; k < nc.n; ++k) {
             const Member& m = nc.m[k];
             const uint64_t nt = tile_count(m);
-            // every tile range must tile [0, bytes) exactly
+            // every tile range must tile [0, bytes) exactly (transpose tiles are 2-D blocks, not byte ranges)
             uint64_t expect = 0;
-            for (uint64_t t = 0; t < nt; ++t) {
+            for (uint64_t t = 0; t < nt && m.mode != kModeTranspose; ++t) {
                 uint64_t lo, hi;
                 tile_range(m, uint32_t(t), &lo, &hi);
                 if (lo != expect || hi <= lo) return set_err(TSNAP_EINVAL, "internal: tile cover broken");
                 expect = hi;
             }
-            if (expect != m.bytes) return set_err(TSNAP_EINVAL, "internal: tile cover incomplete");
+            if (m.mode != kModeTranspose && expect != m.bytes) return set_err(TSNAP_EINVAL, "internal: tile cover incomplete");
             if (host) {
                 out->n_members_host++;
                 out->bytes_host += m.bytes;
+            } else if (m.mode == kModeRows) {
+                out->n_members_rows++;
+                out->n_tiles_rows += nt;
+                out->bytes_rows += m.bytes;
             } else if (m.mode == kModeBulk) {
                 out->n_members_bulk++;
                 out->n_tiles_bulk += nt;

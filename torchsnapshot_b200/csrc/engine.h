@@ -148,10 +148,10 @@ struct Wave {
     uint64_t bytes = 0;       // arena bytes (256B-aligned file regions)
     uint64_t region_off = 0;  // offset of the region inside the arena
     std::vector<Member> members;
-    std::vector<Tile> tiles_bulk, tiles_lsu;
+    std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu;
     void* d_tables = nullptr;
     size_t table_bytes = 0;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr;  // kernel timing
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_kr = nullptr, ev_k2 = nullptr;  // kernel timing: bulk | rows | lsu
     bool timed = false;
     double kernel_ms = 0;
     cudaEvent_t ev_done = nullptr;                                    // kernels finished

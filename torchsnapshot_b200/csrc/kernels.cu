@@ -222,6 +222,188 @@ __global__ void __launch_bounds__(32) tsnap_bulk_copy_kernel(const Member* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// rows kernel: strided members with long 16 B-aligned runs, run by run through the copy engine
+// ------------------------------------------------------------------------------------------------
+// Same ring as the dense kernel (kStages x kStageBytes of shared memory, mbarrier per stage, bulk async-groups
+// for the stores), but warp-collective: a stage holds up to kStageBytes of the member's LOGICAL bytes — a
+// sequence of run segments — and the 32 lanes issue the per-run cp.async.bulk requests in parallel.  A side
+// whose runs are adjacent (the wire image on save, the file image on restore) is moved with ONE request per
+// stage.  No data passes through registers (SASS: UBLKCP.S.G / UBLKCP.G.S only).
+struct RowsPiece {
+    uint32_t member;  // index into the member table
+    uint64_t pos;     // logical byte position inside the member
+    uint32_t n;       // logical bytes
+};
+
+struct RowsCursor {
+    const Member* members;
+    const Tile* tiles;
+    uint32_t ntiles, tile, stride;
+    uint64_t pos, end;
+    uint32_t member;
+    bool open;
+};
+
+__device__ __forceinline__ bool rows_next(RowsCursor& c, uint32_t stage_bytes, RowsPiece* out) {
+    while (true) {
+        if (c.open && c.pos < c.end) {
+            uint64_t n = c.end - c.pos;
+            if (n > stage_bytes) n = stage_bytes;
+            out->member = c.member;
+            out->pos = c.pos;
+            out->n = (uint32_t)n;
+            c.pos += n;
+            return true;
+        }
+        if (c.open) c.tile += c.stride;
+        if (c.tile >= c.ntiles) return false;
+        const Tile t = c.tiles[c.tile];
+        c.member = t.member;
+        const uint64_t mbytes = c.members[t.member].bytes;
+        c.pos = (uint64_t)t.index * kTileBulk;
+        c.end = c.pos + kTileBulk;
+        if (c.end > mbytes) c.end = mbytes;
+        c.open = true;
+    }
+}
+
+__device__ __forceinline__ void rows_offsets(const Member& m, uint64_t row, int64_t* so, int64_t* dofs) {
+    if (m.nouter == 1) {
+        *so = (int64_t)row * m.sstride[0];
+        *dofs = (int64_t)row * m.dstride[0];
+        return;
+    }
+    int64_t s = 0, d = 0;
+    for (int i = (int)m.nouter - 1; i >= 0; --i) {
+        const uint64_t sz = (uint64_t)m.osize[i];
+        const uint64_t idx = row % sz;
+        row /= sz;
+        s += (int64_t)idx * m.sstride[i];
+        d += (int64_t)idx * m.dstride[i];
+    }
+    *so = s;
+    *dofs = d;
+}
+
+// issues the copy-engine requests of one piece on one side.  kLoad: global -> stage (completion on `bar`),
+// else stage -> global (bulk async-group of the issuing lane).
+template <bool kLoad>
+__device__ __forceinline__ void rows_issue(const Member& m, uint64_t pos, uint32_t n, uint32_t stage_smem, uint32_t bar,
+                                           uint64_t policy, uint32_t lane) {
+    const bool dense = (m.shift & (kLoad ? kRowsSrcDense : kRowsDstDense)) != 0;
+    if (dense) {
+        if (lane == 0) {
+            if (kLoad) bulk_g2s(stage_smem, reinterpret_cast<const char*>(m.src) + pos, n, bar, policy);
+            else bulk_s2g(reinterpret_cast<char*>(m.dst) + pos, stage_smem, n);
+        }
+        return;
+    }
+    const uint64_t inner = m.inner;
+    const uint64_t row0 = pos / inner;
+    const uint64_t col0 = pos - row0 * inner;
+    uint64_t len0 = inner - col0;
+    if (len0 > n) len0 = n;
+    const uint32_t nseg = 1 + (uint32_t)((n - len0 + inner - 1) / inner);
+    for (uint32_t k = lane; k < nseg; k += 32) {
+        const uint64_t seg_off = k == 0 ? 0 : len0 + (uint64_t)(k - 1) * inner;  // inside the stage
+        uint64_t len = k == 0 ? len0 : inner;
+        if (seg_off + len > n) len = n - seg_off;
+        int64_t so, dofs;
+        rows_offsets(m, row0 + k, &so, &dofs);
+        const uint64_t col = k == 0 ? col0 : 0;
+        if (kLoad) bulk_g2s(stage_smem + (uint32_t)seg_off, reinterpret_cast<const char*>(m.src) + so + col, (uint32_t)len, bar, policy);
+        else bulk_s2g(reinterpret_cast<char*>(m.dst) + dofs + col, stage_smem + (uint32_t)seg_off, (uint32_t)len);
+    }
+}
+
+template <int kStages, int kStageBytes>
+__global__ void __launch_bounds__(32) tsnap_rows_copy_kernel(const Member* __restrict__ members,
+                                                             const Tile* __restrict__ tiles, uint32_t ntiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [kStages * kStageBytes data][kStages member records][kStages mbarriers]
+    unsigned char* data = smem_raw;
+    Member* st_m = reinterpret_cast<Member*>(smem_raw + kStages * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_m + kStages);
+    const uint32_t lane = threadIdx.x;
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    __syncwarp();
+    const uint64_t policy = policy_evict_first();
+
+    RowsCursor cur;
+    cur.members = members;
+    cur.tiles = tiles;
+    cur.ntiles = ntiles;
+    cur.tile = blockIdx.x;
+    cur.stride = gridDim.x;
+    cur.open = false;
+    cur.pos = cur.end = 0;
+    cur.member = 0;
+
+    uint64_t st_pos[kStages];
+    uint32_t st_n[kStages];
+    uint32_t issued = 0, stored = 0;
+
+    // stage `s` <- piece `p`: the member record travels with the stage (loads of the next member are in flight while
+    // the previous member's stage is being stored)
+    auto load_piece = [&](int s, const RowsPiece& p) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(members + p.member);
+        uint32_t* d = reinterpret_cast<uint32_t*>(&st_m[s]);
+        for (uint32_t i = lane; i < sizeof(Member) / 4; i += 32) d[i] = g[i];
+        const uint32_t bar = smem_u32(&bars[s]);
+        if (lane == 0) mbar_expect_tx(bar, p.n);
+        __syncwarp();
+        rows_issue<true>(st_m[s], p.pos, p.n, smem_u32(data + s * kStageBytes), bar, policy, lane);
+    };
+
+    RowsPiece p;
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+        if (issued == (uint32_t)s && rows_next(cur, kStageBytes, &p)) {
+            load_piece(s, p);
+            st_pos[s] = p.pos;
+            st_n[s] = p.n;
+            ++issued;
+        }
+    }
+    while (stored < issued) {
+        const uint32_t s = stored % kStages;
+        mbar_wait(smem_u32(&bars[s]), (stored / kStages) & 1);
+        fence_proxy_async_smem();
+        uint64_t pos = 0;
+        uint32_t n = 0;
+#pragma unroll
+        for (int k = 0; k < kStages; ++k)
+            if (k == (int)s) {
+                pos = st_pos[k];
+                n = st_n[k];
+            }
+        rows_issue<false>(st_m[s], pos, n, smem_u32(data + s * kStageBytes), 0, policy, lane);
+        bulk_commit();
+        ++stored;
+        if (stored >= 2) {
+            bulk_wait_read<1>();  // every lane: all but its newest store group have finished reading shared memory
+            __syncwarp();
+            if (rows_next(cur, kStageBytes, &p)) {
+                const uint32_t fs = (stored - 2) % kStages;
+                load_piece((int)fs, p);
+#pragma unroll
+                for (int k = 0; k < kStages; ++k)
+                    if (k == (int)fs) {
+                        st_pos[k] = p.pos;
+                        st_n[k] = p.n;
+                    }
+                ++issued;
+            }
+        }
+    }
+    bulk_wait_all<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSU kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kLsuThreads = 256;
@@ -434,6 +616,55 @@ __device__ __noinline__ void tile_strided(const Member& m, uint32_t index) {
     }
 }
 
+// ---- tiled transpose ---------------------------------------------------------------------------
+// kModeTranspose: dim A is unit-stride on the source, dim B on the destination.  One tile = side x side elements of
+// (A, B) for one index of the remaining dims: read with consecutive threads along A, write with consecutive threads
+// along B, through a padded shared-memory tile — both sides see full-line accesses instead of an element gather.
+template <typename T, int kSide>
+__device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index, unsigned char* tbuf) {
+    const uint32_t A = m.shift & 255, B = (m.shift >> 8) & 255;
+    const uint64_t sA = (uint64_t)m.osize[A], sB = (uint64_t)m.osize[B];
+    const uint32_t tilesA = (uint32_t)((sA + kSide - 1) / kSide), tilesB = (uint32_t)((sB + kSide - 1) / kSide);
+    const uint32_t ib = index % tilesB;
+    uint32_t rest = index / tilesB;
+    const uint32_t ia = rest % tilesA;
+    rest /= tilesA;
+    int64_t so = 0, dofs = 0;
+    for (int i = (int)m.nouter - 1; i >= 0; --i) {
+        if ((uint32_t)i == A || (uint32_t)i == B) continue;
+        const uint32_t sz = (uint32_t)m.osize[i];
+        const uint32_t idx = rest % sz;
+        rest /= sz;
+        so += (int64_t)idx * m.sstride[i];
+        dofs += (int64_t)idx * m.dstride[i];
+    }
+    const uint64_t a0 = (uint64_t)ia * kSide, b0 = (uint64_t)ib * kSide;
+    const uint32_t na = (uint32_t)(sA - a0 < (uint64_t)kSide ? sA - a0 : kSide);
+    const uint32_t nb = (uint32_t)(sB - b0 < (uint64_t)kSide ? sB - b0 : kSide);
+    const char* sp = reinterpret_cast<const char*>(m.src) + so + (int64_t)a0 * m.sstride[A] + (int64_t)b0 * m.sstride[B];
+    char* dp = reinterpret_cast<char*>(m.dst) + dofs + (int64_t)a0 * m.dstride[A] + (int64_t)b0 * m.dstride[B];
+    T(*tile)[kSide + 1] = reinterpret_cast<T(*)[kSide + 1]>(tbuf);
+    constexpr int kRowsPerPass = kLsuThreads / kSide;
+    const uint32_t tx = threadIdx.x % kSide, ty = threadIdx.x / kSide;
+    // read: tx runs along A (contiguous source), rows along B
+    for (uint32_t b = ty; b < nb; b += kRowsPerPass)
+        if (tx < na) tile[b][tx] = __ldg(reinterpret_cast<const T*>(sp + (int64_t)b * m.sstride[B]) + tx);
+    __syncthreads();
+    // write: tx runs along B (contiguous destination), rows along A
+    for (uint32_t a = ty; a < na; a += kRowsPerPass)
+        if (tx < nb) reinterpret_cast<T*>(dp + (int64_t)a * m.dstride[A])[tx] = tile[tx][a];
+    // the caller's loop synchronises before the tile buffer is reused
+}
+
+__device__ __noinline__ void tile_transpose(const Member& m, uint32_t index, unsigned char* tbuf) {
+    switch (m.unit) {
+        case 8: tile_transpose_t<uint64_t, 64>(m, index, tbuf); break;
+        case 4: tile_transpose_t<uint32_t, 64>(m, index, tbuf); break;
+        case 2: tile_transpose_t<uint16_t, 128>(m, index, tbuf); break;
+        default: tile_transpose_t<uint8_t, 128>(m, index, tbuf); break;
+    }
+}
+
 // ---- fused cast -------------------------------------------------------------------------------
 __device__ __forceinline__ double load_elem(const char* p, uint32_t dt) {
     switch (dt) {
@@ -554,6 +785,7 @@ __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
 __global__ void __launch_bounds__(kLsuThreads, 3) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
                                                                    const Tile* __restrict__ tiles, uint32_t ntiles) {
     __shared__ Member sm;
+    __shared__ __align__(16) unsigned char tbuf[64 * 65 * 8];  // transpose tile: 64 x 65 x 8 B >= 128 x 129 x 2 B
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const Tile tl = tiles[t];
         // stage the member record in shared memory: every thread needs all of it
@@ -568,6 +800,7 @@ __global__ void __launch_bounds__(kLsuThreads, 3) tsnap_lsu_copy_kernel(const Me
             case kModeContig: tile_contig(sm, tl.index); break;
             case kModeStrided: tile_strided(sm, tl.index); break;
             case kModeCast: tile_cast(sm, tl.index); break;
+            case kModeTranspose: tile_transpose(sm, tl.index, tbuf); break;
             default: {
                 // a bulk-mode member routed here (never emitted by the planner when bulk is disabled,
                 // kept for robustness): dense and 16B aligned on both sides
@@ -584,55 +817,51 @@ __global__ void __launch_bounds__(kLsuThreads, 3) tsnap_lsu_copy_kernel(const Me
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-// Ring geometry of the bulk kernel.  Default picked by measurement on B200 (profiles/r01_ncu_summary.md);
-// TSNAP_B200_BULK_CFG selects an alternative for A/B runs.
+// Ring geometry of the copy-engine kernels, picked by a 10-point sweep on B200 (profiles/r01_ncu_summary.md): two
+// 48 KiB stages per one-warp CTA, two CTAs per SM (0.98 of the measured copy peak).  TSNAP_B200_BULK_CFG=0 selects the
+// first version's geometry (3 x 16 KiB, 4 CTAs per SM; 0.95) for A/B runs.
 struct BulkCfg {
     int stages, stage_bytes, ctas_per_sm;
 };
 static const BulkCfg kBulkCfgs[] = {
-    {3, 16384, 4},  // 0: first version — 48 KiB per CTA, 192 KiB per SM (0.95 of the measured copy peak)
-    {4, 8192, 6},   // 1
-    {2, 32768, 3},  // 2
-    {4, 16384, 3},  // 3
-    {6, 8192, 4},   // 4
-    {3, 32768, 2},  // 5
-    {2, 49152, 2},  // 6: default — two 48 KiB stages per CTA, two CTAs per SM (0.98)
-    {3, 24576, 3},  // 7
-    {2, 65536, 1},  // 8
-    {4, 32768, 1},  // 9
+    {3, 16384, 4},  // 0: fallback
+    {2, 49152, 2},  // 1: default
 };
 static int bulk_cfg_index() {
     static const int idx = [] {
         const char* e = getenv("TSNAP_B200_BULK_CFG");
-        const int n = int(sizeof(kBulkCfgs) / sizeof(kBulkCfgs[0]));
-        const int v = e ? atoi(e) : 6;
-        return v >= 0 && v < n ? v : 6;
+        return e && atoi(e) == 0 ? 0 : 1;
     }();
     return idx;
 }
 
 template <int S, int B>
 static cudaError_t bulk_attr() {
-    return cudaFuncSetAttribute(tsnap_bulk_copy_kernel<S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * B + S * 8);
+    cudaError_t e = cudaFuncSetAttribute(tsnap_bulk_copy_kernel<S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * B + S * 8);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(tsnap_rows_copy_kernel<S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * B + S * (int)sizeof(Member) + S * 8);
+    return e;
 }
 template <int S, int B>
 static void bulk_launch(const Member* m, const Tile* t, uint32_t n, uint32_t grid, cudaStream_t st) {
     tsnap_bulk_copy_kernel<S, B><<<grid, 32, S * B + S * 8, st>>>(m, t, n);
 }
+template <int S, int B>
+static void rows_launch(const Member* m, const Tile* t, uint32_t n, uint32_t grid, cudaStream_t st) {
+    tsnap_rows_copy_kernel<S, B><<<grid, 32, S * B + S * (int)sizeof(Member) + S * 8, st>>>(m, t, n);
+}
 
-constexpr int kLsuCtasPerSm = 6;
+// resident CTAs per SM of the LSU kernel, from the occupancy calculator: the persistent grid is exactly one wave
+static int g_lsu_ctas_per_sm = 3;
 
 cudaError_t init_kernels() {
     cudaError_t e = bulk_attr<3, 16384>();
-    if (e == cudaSuccess) e = bulk_attr<4, 8192>();
-    if (e == cudaSuccess) e = bulk_attr<2, 32768>();
-    if (e == cudaSuccess) e = bulk_attr<4, 16384>();
-    if (e == cudaSuccess) e = bulk_attr<6, 8192>();
-    if (e == cudaSuccess) e = bulk_attr<3, 32768>();
     if (e == cudaSuccess) e = bulk_attr<2, 49152>();
-    if (e == cudaSuccess) e = bulk_attr<3, 24576>();
-    if (e == cudaSuccess) e = bulk_attr<2, 65536>();
-    if (e == cudaSuccess) e = bulk_attr<4, 32768>();
+    if (e == cudaSuccess) {
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel, kLsuThreads, 0);
+        if (e == cudaSuccess && n > 0) g_lsu_ctas_per_sm = n;
+    }
     return e;
 }
 
@@ -642,25 +871,26 @@ cudaError_t launch_bulk(const Member* d_members, const Tile* d_tiles, uint32_t n
     const int ci = bulk_cfg_index();
     uint32_t grid = (uint32_t)sm_count * kBulkCfgs[ci].ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
-    switch (ci) {
-        case 1: bulk_launch<4, 8192>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 2: bulk_launch<2, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 3: bulk_launch<4, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 4: bulk_launch<6, 8192>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 5: bulk_launch<3, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 7: bulk_launch<3, 24576>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 8: bulk_launch<2, 65536>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 9: bulk_launch<4, 32768>(d_members, d_tiles, ntiles, grid, stream); break;
-        case 0: bulk_launch<3, 16384>(d_members, d_tiles, ntiles, grid, stream); break;
-        default: bulk_launch<2, 49152>(d_members, d_tiles, ntiles, grid, stream); break;
-    }
+    if (ci == 0) bulk_launch<3, 16384>(d_members, d_tiles, ntiles, grid, stream);
+    else bulk_launch<2, 49152>(d_members, d_tiles, ntiles, grid, stream);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rows(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
+                        cudaStream_t stream) {
+    if (ntiles == 0) return cudaSuccess;
+    const int ci = bulk_cfg_index();
+    uint32_t grid = (uint32_t)sm_count * kBulkCfgs[ci].ctas_per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (ci == 0) rows_launch<3, 16384>(d_members, d_tiles, ntiles, grid, stream);
+    else rows_launch<2, 49152>(d_members, d_tiles, ntiles, grid, stream);
     return cudaGetLastError();
 }
 
 cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
                        cudaStream_t stream) {
     if (ntiles == 0) return cudaSuccess;
-    uint32_t grid = (uint32_t)sm_count * kLsuCtasPerSm;
+    uint32_t grid = (uint32_t)sm_count * (uint32_t)g_lsu_ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
     tsnap_lsu_copy_kernel<<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
     return cudaGetLastError();

@@ -1,6 +1,7 @@
 #include "plan.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace tsnap {
@@ -21,9 +22,26 @@ bool cast_supported(int s, int d) {
 
 static inline uint64_t lowbit(uint64_t x) { return x & (~x + 1); }
 
+// TSNAP_B200_ROWS_MIN_RUN: shortest contiguous run (bytes) that is handed to the copy engine run by run (A/B knob)
+static uint64_t rows_min_run() {
+    static const uint64_t v = [] {
+        const char* e = getenv("TSNAP_B200_ROWS_MIN_RUN");
+        const long long x = e ? atoll(e) : 0;
+        return x >= 16 ? uint64_t(x) : kRowsMinRun;
+    }();
+    return v;
+}
+
 struct Dim {
     int64_t size, ss, ds;  // strides in bytes
 };
+
+static bool tile_fits_u32(const Member& m, int a, int b, uint32_t esz) {
+    const uint32_t side = transpose_side(esz);
+    long double n = 1;
+    for (uint32_t i = 0; i < m.nouter; ++i) n *= (int(i) == a || int(i) == b) ? (long double)((uint64_t(m.osize[i]) + side - 1) / side) : (long double)m.osize[i];
+    return n < 4.0e9L;
+}
 
 int normalize_copy(const tsnap_copy_desc& d, uint64_t wire_base, bool allow_bulk, NormalizedCopy* out,
                    std::string* err) {
@@ -153,10 +171,48 @@ int normalize_copy(const tsnap_copy_desc& d, uint64_t wire_base, bool allow_bulk
         out->n = 1;
         return TSNAP_OK;
     }
+    if (m.inner == ed && nd >= 2 && nd <= kMaxOuter) {
+        // No run is contiguous on both sides.  If the source is unit-stride along one dim and the destination along
+        // another (t(), permute of a dense tensor), tile over those two dims through shared memory.
+        int a = -1, b = -1;
+        for (int i = 0; i < nd; ++i) {
+            if (m.sstride[i] == int64_t(es) && a < 0) a = i;
+            if (m.dstride[i] == int64_t(ed) && b < 0) b = i;
+        }
+        bool aligned = (m.src % es) == 0 && (m.dst % ed) == 0;
+        for (int i = 0; i < nd; ++i) aligned = aligned && (uint64_t(m.sstride[i]) % es) == 0 && (uint64_t(m.dstride[i]) % ed) == 0;
+        const bool device_copy = d.src_space != TSNAP_SPACE_HOST && d.dst_space != TSNAP_SPACE_HOST;
+        if (device_copy && aligned && a >= 0 && b >= 0 && a != b && m.osize[a] >= 16 && m.osize[b] >= 16 && tile_fits_u32(m, a, b, uint32_t(ed))) {
+            m.mode = kModeTranspose;
+            m.unit = uint32_t(ed);
+            m.shift = uint32_t(a) | (uint32_t(b) << 8);
+            out->m[0] = m;
+            out->n = 1;
+            return TSNAP_OK;
+        }
+    }
     m.mode = kModeStrided;
     uint64_t bits = 16 | m.inner | m.src | m.dst;
     for (int i = 0; i < nd; ++i) bits |= uint64_t(m.sstride[i]) | uint64_t(m.dstride[i]);
     m.unit = uint32_t(lowbit(bits));
+    {
+        // Column shards / narrow on dim != 0 of wide tables (T:io_preparers/sharded_tensor.py:76, torchrec COLUMN_WISE)
+        // and reshard boxes have long 16 B-aligned runs: those go to the copy engine run by run.
+        const bool device_copy = d.src_space != TSNAP_SPACE_HOST && d.dst_space != TSNAP_SPACE_HOST;
+        if (allow_bulk && device_copy && m.unit == 16 && m.inner >= rows_min_run()) {
+            m.mode = kModeRows;
+            // is a side laid out run after run (the wire side always is)?
+            uint64_t accs = m.inner, accd = m.inner;
+            bool sd = true, dd = true;
+            for (int i = nd - 1; i >= 0; --i) {
+                sd = sd && uint64_t(m.sstride[i]) == accs;
+                dd = dd && uint64_t(m.dstride[i]) == accd;
+                accs *= uint64_t(m.osize[i]);
+                accd *= uint64_t(m.osize[i]);
+            }
+            m.shift = (sd ? kRowsSrcDense : 0) | (dd ? kRowsDstDense : 0);
+        }
+    }
     out->m[0] = m;
     out->n = 1;
     return TSNAP_OK;
@@ -231,7 +287,7 @@ void host_copy_range(const Member& m, uint64_t lo, uint64_t hi) {
         std::memcpy(dst + lo, src + lo, hi - lo);
         return;
     }
-    if (m.mode == kModeStrided) {
+    if (m.mode == kModeStrided || m.mode == kModeRows || m.mode == kModeTranspose) {
         uint64_t pos = lo;
         while (pos < hi) {
             const uint64_t row = pos / m.inner, col = pos % m.inner;

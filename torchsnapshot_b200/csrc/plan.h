@@ -26,7 +26,14 @@ enum Mode : uint32_t {
     kModeContig = 1,   // contiguous both sides, arbitrary alignment -> 16B stores + (shifted) loads
     kModeStrided = 2,  // outer dims x inner contiguous run, `unit`-byte granules
     kModeCast = 3,     // element-wise dtype conversion, strided both sides
+    kModeTranspose = 5,  // no run is contiguous on both sides, but each side has a unit-stride dimension (a.t(), permute):
+                         // shared-memory tiled transpose over those two dims, coalesced on both sides
+    kModeRows = 4,     // kModeStrided whose runs, strides and bases are all multiples of 16 B and whose runs are long
+                       // enough for the copy engine: one cp.async.bulk per run (or one per stage on a dense side)
 };
+constexpr uint32_t kRowsSrcDense = 1;  // Member.shift bits in kModeRows: consecutive runs are adjacent on that side
+constexpr uint32_t kRowsDstDense = 2;
+constexpr uint64_t kRowsMinRun = 256;  // shorter runs stay on the LSU path (one copy-engine request per run does not pay)
 
 // Device-visible member record.  Addresses are absolute for the space they live in.
 struct alignas(16) Member {
@@ -37,7 +44,8 @@ struct alignas(16) Member {
     uint32_t mode;
     uint32_t unit;    // kModeStrided: granule bytes (1,2,4,8,16)
     uint32_t nouter;
-    uint32_t shift;   // kModeContig: dst & 15 (tile boundaries are dst-16B aligned)
+    uint32_t shift;   // kModeContig: dst & 15 (tile boundaries are dst-16B aligned); kModeRows: kRows*Dense flags;
+                      // kModeTranspose: index of the src-contiguous dim | index of the dst-contiguous dim << 8
     uint32_t src_dtype;
     uint32_t dst_dtype;
     uint32_t src_esz;
@@ -52,19 +60,29 @@ struct Tile {
     uint32_t index;   // tile ordinal within the member
 };
 
-inline uint32_t tile_bytes_for(uint32_t mode) { return mode == kModeBulk ? kTileBulk : kTileLsu; }
+inline bool engine_mode(uint32_t mode) { return mode == kModeBulk || mode == kModeRows; }  // copy-engine kernels
+inline uint32_t tile_bytes_for(uint32_t mode) { return engine_mode(mode) ? kTileBulk : kTileLsu; }
+
+// kModeTranspose: elements per tile side (a tile is side x side elements of the two unit-stride dims)
+inline uint32_t transpose_side(uint32_t esz) { return esz >= 4 ? 64 : 128; }
 
 // number of tiles a member needs
 inline uint64_t tile_count(const Member& m) {
     if (m.bytes == 0) return 0;
-    if (m.mode == kModeBulk) return (m.bytes + kTileBulk - 1) / kTileBulk;
+    if (m.mode == kModeTranspose) {
+        const uint32_t a = m.shift & 255, b = (m.shift >> 8) & 255, side = transpose_side(m.unit);
+        uint64_t n = 1;
+        for (uint32_t i = 0; i < m.nouter; ++i) n *= (i == a || i == b) ? (uint64_t(m.osize[i]) + side - 1) / side : uint64_t(m.osize[i]);
+        return n;
+    }
+    if (engine_mode(m.mode)) return (m.bytes + kTileBulk - 1) / kTileBulk;
     if (m.mode == kModeContig) return (m.bytes + m.shift + kTileLsu - 1) / kTileLsu;
     return (m.bytes + kTileLsu - 1) / kTileLsu;
 }
 
 // logical byte range [lo, hi) of tile `index` of member m  (host+device identical: see kernels.cu)
 inline void tile_range(const Member& m, uint32_t index, uint64_t* lo, uint64_t* hi) {
-    if (m.mode == kModeBulk) {
+    if (engine_mode(m.mode)) {
         *lo = uint64_t(index) * kTileBulk;
         *hi = *lo + kTileBulk;
     } else if (m.mode == kModeContig) {

@@ -87,7 +87,9 @@ class TensorBufferStager(BufferStager):
         t = self.source()
         if t.numel() == 0:
             return [], []
-        if self.is_async_snapshot and t.device.type == "cpu":
+        if _native.needs_contiguous_copy(t):
+            t = t.contiguous()
+        elif self.is_async_snapshot and t.device.type == "cpu":
             # host memory is read while the snapshot drains in the background: take a private copy so
             # that later in-place updates (e.g. Adam's CPU `step` counters) cannot leak into it
             t = t.clone()

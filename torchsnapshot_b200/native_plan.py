@@ -42,16 +42,24 @@ def _describe_tensor_stager(st: Any, offset: int) -> Optional[Described]:
         return None
     t = tensor.detach()
     func = getattr(st, "_tensor_prepare_func", None)
+    wire_dtype = None
     if func is not None:
-        t = func(t, False).detach()  # persist the processed tensor
-    if str(t.dtype) != entry.dtype or list(t.shape) != list(entry.shape):
+        from .prepare import fused_cast_of
+
+        wire_dtype = fused_cast_of(func, t)
+        if wire_dtype is None:
+            t = func(t, False).detach()  # persist the processed tensor
+        # else: a pure float cast — the pack kernel converts while it gathers, no processed tensor is materialised
+    if str(wire_dtype or t.dtype) != entry.dtype or list(t.shape) != list(entry.shape):
         return None
     nbytes = _entry_nbytes(entry)
     if t.numel() == 0:
         return [], [], nbytes
-    if getattr(st, "is_async_snapshot", False) and t.device.type == "cpu":
+    if _native.needs_contiguous_copy(t):
+        t = t.contiguous()
+    elif getattr(st, "is_async_snapshot", False) and t.device.type == "cpu":
         t = t.clone()  # host memory is read after async_take returned
-    return [_native.save_desc(t, offset)], [t], nbytes
+    return [_native.save_desc(t, offset, wire_dtype=wire_dtype)], [t], nbytes
 
 
 def describe_stager(st: Any) -> Optional[Described]:

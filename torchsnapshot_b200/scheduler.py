@@ -39,19 +39,21 @@ _AVAILABLE_MEMORY_MULTIPLIER = 0.6
 _MAX_PER_RANK_CPU_CONCURRENCY = 4
 
 
-_LOCAL_WORLD: Dict[Tuple[int, int], int] = {}
+_LOCAL_WORLD: Dict[int, Tuple[object, int]] = {}  # id(pg) -> (pg kept alive so the id stays unique, ranks on this host)
 
 
 def get_local_world_size(pg: PGWrapper) -> int:
     """Ranks of `pg` on this host (T:scheduler.py:35-44).  Host placement does not change during a job, so the
     hostname all-gather is paid once per process group instead of once per snapshot."""
-    key = (id(pg.pg), pg.get_world_size())
-    if key not in _LOCAL_WORLD:
+    key = id(pg.pg)
+    ent = _LOCAL_WORLD.get(key)
+    if ent is None or ent[0] is not pg.pg:
         me = socket.gethostname()
         names = [None] * pg.get_world_size()
         pg.all_gather_object(names, me)
-        _LOCAL_WORLD[key] = sum(1 for n in names if n == me)
-    return _LOCAL_WORLD[key]
+        ent = (pg.pg, sum(1 for n in names if n == me))
+        _LOCAL_WORLD[key] = ent
+    return ent[1]
 
 
 def get_process_memory_budget_bytes(pg: PGWrapper) -> int:

@@ -425,19 +425,25 @@ class Snapshot:
 
 # ---- async commit ------------------------------------------------------------------------------------
 _store_lock = threading.Lock()
-_store_cache: Dict[int, Any] = {}
-_take_seq = itertools.count()
+# id(pg) -> [pg, store, takes so far].  The entry holds the process group itself, so its id cannot be reused by a
+# later group while the entry exists; an entry whose group object differs is stale and replaced.
+_store_cache: Dict[int, List[Any]] = {}
 
 
 def _commit_store(pgw: PGWrapper):
-    """A key-value store reachable by all ranks of `pgw`, usable from a background thread (collectives are
-    not).  Rank 0 hosts a TCPStore; its address travels by broadcast once per process group."""
+    """(store, tag) for the commit rendezvous of one async_take on `pgw`: a key-value store reachable by all its
+    ranks and usable from a background thread (collectives are not), and a tag every rank derives identically —
+    the number of async takes issued on THIS process group (a process-global counter would diverge between ranks
+    that took a different number of snapshots on other groups).  Rank 0 hosts a TCPStore; its address travels by
+    broadcast once per process group."""
     if pgw.get_world_size() == 1:
-        return None
+        return None, ""
     key = id(pgw.pg)
     with _store_lock:
-        if key in _store_cache:
-            return _store_cache[key]
+        ent = _store_cache.get(key)
+        if ent is not None and ent[0] is pgw.pg:
+            ent[2] += 1
+            return ent[1], f"tsnap_b200/take{ent[2]}"
     box: List[Any] = [None]
     if pgw.get_rank() == 0:
         sock = socket.socket()
@@ -450,8 +456,8 @@ def _commit_store(pgw: PGWrapper):
     host, port = box[0]
     store = dist.TCPStore(host, port, pgw.get_world_size(), pgw.get_rank() == 0, timedelta(seconds=1800), wait_for_workers=False)
     with _store_lock:
-        _store_cache[key] = store
-    return store
+        _store_cache[key] = [pgw.pg, store, 0]
+    return store, "tsnap_b200/take0"
 
 
 class PendingSnapshot:
@@ -475,8 +481,7 @@ class PendingSnapshot:
         self._metadata = metadata
         self.exc_info: Optional[Any] = None
         self._done = False
-        store = _commit_store(pgw)  # collective: must happen on the caller thread
-        tag = f"tsnap_b200/{path}#{next(_take_seq)}"
+        store, tag = _commit_store(pgw)  # collective on first use: must happen on the caller thread
         self.thread = threading.Thread(
             target=self._complete, args=(pending_io_work, pgw.get_rank(), pgw.get_world_size(), metadata, storage, loop, store, tag), daemon=True
         )
@@ -506,6 +511,13 @@ class PendingSnapshot:
                     store.set(f"{tag}/depart", "ok" if not bad else bad[0])
                 store.wait([f"{tag}/depart"], self.DEFAULT_BARRIER_TIMEOUT)
                 verdict = store.get(f"{tag}/depart").decode()
+                # the last rank to learn the verdict clears the rendezvous keys
+                if store.add(f"{tag}/left", 1) == world:
+                    for k in [f"{tag}/arrive/{r}" for r in range(world)] + [f"{tag}/depart", f"{tag}/left"]:
+                        try:
+                            store.delete_key(k)
+                        except Exception:
+                            pass
                 if verdict != "ok" and err is None:
                     raise RuntimeError(f"snapshot aborted by a peer: {verdict}")
         except Exception:
