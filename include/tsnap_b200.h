@@ -270,6 +270,13 @@ int tsnap_buffer_get_stats(tsnap_buffer* buf, tsnap_job_stats* out);
 int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes,
                   const tsnap_copy_desc* members, int32_t n_members, void* consumer_stream);
 
+/* scatter a wire image that is ALREADY in device memory (e.g. received from a peer GPU over NVLink: one rank reads a
+ * replicated file from storage, ncclBroadcast delivers it, every rank scatters it — "read once" restore of DDP state,
+ * which the reference re-reads from storage on every rank, T:manifest_ops.py:69-85).  Same members as tsnap_consume,
+ * desc->src_addr relative to `device_wire`.  Ordered after `consumer_stream`; synchronous. */
+int tsnap_scatter_device(tsnap_engine* eng, const void* device_wire, uint64_t nbytes,
+                         const tsnap_copy_desc* members, int32_t n_members, void* consumer_stream);
+
 /* ---- planning introspection (host only; used by the CPU test-suite) -----------------------------
  * Normalises `members` exactly as a job would and reports the tile decomposition. */
 typedef struct tsnap_plan_info {

@@ -20,7 +20,7 @@ local = W.build_llama_local(0, 1, dev)
 payload = sum(t.numel() * t.element_size() for t, _, _ in local.values())
 app = {"model": B.StateDict(**W.wrap_sharded(local, 0, dev))}
 root = tempfile.mkdtemp(prefix="sweep_", dir=args.dir)
-KEYS = ("TSNAP_B200_IO_THREADS", "TSNAP_B200_PINNED_SLOTS", "TSNAP_B200_PINNED_SLOT_BYTES", "TSNAP_B200_IO_PIN", "TSNAP_B200_ENGINE_FLAGS", "TSNAP_B200_HBM_STAGING_BYTES", "TSNAP_B200_NUMA")
+KEYS = ("TSNAP_B200_IO_THREADS", "TSNAP_B200_PINNED_SLOTS", "TSNAP_B200_PINNED_SLOT_BYTES", "TSNAP_B200_IO_PIN", "TSNAP_B200_ENGINE_FLAGS", "TSNAP_B200_HBM_STAGING_BYTES", "TSNAP_B200_NUMA", "TSNAP_B200_RING_NUMA")
 
 def run(tag, env, do_async=False):
     for k in KEYS: os.environ.pop(k, None)
@@ -65,6 +65,18 @@ if args.set in ("all", "threads"):
     for t in (16, 24, 32):
         run(f"t{t} spread", {**base, "TSNAP_B200_IO_THREADS": t, "TSNAP_B200_IO_PIN": "spread"})
     run("t16 local", {**base, "TSNAP_B200_IO_PIN": "local"})
+if args.set in ("all", "numa"):
+    # placement of the pinned ring x placement of the workers; every combination twice (a fresh ring each time:
+    # without explicit placement the ring lands wherever the allocating thread happens to run)
+    for rep in range(2):
+        for ring in ("none", "gpu", "interleave"):
+            for pin in ("none", "node", "spread", "local"):
+                if (ring, pin) in (("interleave", "local"),):
+                    continue
+                run(f"ring={ring} pin={pin} #{rep}", {**base, "TSNAP_B200_RING_NUMA": ring, "TSNAP_B200_IO_PIN": pin})
+    for t in (12, 20, 24):
+        run(f"ring=interleave pin=node t{t}", {**base, "TSNAP_B200_IO_THREADS": t, "TSNAP_B200_RING_NUMA": "interleave", "TSNAP_B200_IO_PIN": "node"})
+    run("ring=interleave pin=node no_arena", {**base, "TSNAP_B200_RING_NUMA": "interleave", "TSNAP_B200_IO_PIN": "node", "TSNAP_B200_ENGINE_FLAGS": N.ENGINE_NO_ARENA})
 if args.set in ("all", "ring"):
     for sb, n in ((8, 256), (16, 128), (64, 32), (32, 32), (32, 128)):
         run(f"slots {n}x{sb}MiB", {**base, "TSNAP_B200_PINNED_SLOTS": n, "TSNAP_B200_PINNED_SLOT_BYTES": sb * MiB})

@@ -199,6 +199,7 @@ EXPORTED_SYMBOLS = [
     "tsnap_job_set_arena",
     "tsnap_job_get_trace",
     "tsnap_engine_probe",
+    "tsnap_scatter_device",
 ]
 
 
@@ -243,6 +244,7 @@ def _load() -> C.CDLL:
     lib.tsnap_job_set_arena.argtypes = [vp, vp, C.c_uint64]
     lib.tsnap_job_get_trace.argtypes = [vp, C.POINTER(TraceRec), C.c_uint64, C.POINTER(C.c_uint64)]
     lib.tsnap_engine_probe.argtypes = [vp, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_double)]
+    lib.tsnap_scatter_device.argtypes = [vp, vp, C.c_uint64, C.POINTER(CopyDesc), C.c_int32, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tsnap_last_error", "tsnap_dtype_size"):
@@ -603,6 +605,15 @@ class Engine:
         if stream is None and self.device >= 0:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         check(lib.tsnap_consume(self._h, C.c_void_p(addr), n, arr, len(descs), C.c_void_p(stream or 0)))
+
+    def scatter_device(self, wire: torch.Tensor, descs: Sequence[CopyDesc], stream: Optional[int] = None) -> None:
+        """Scatter a wire image that already sits in this GPU's memory (`wire`: uint8 CUDA tensor) into destination views."""
+        if not descs:
+            return
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        arr = _desc_array(descs)
+        check(lib.tsnap_scatter_device(self._h, C.c_void_p(wire.data_ptr()), wire.numel() * wire.element_size(), arr, len(descs), C.c_void_p(stream or 0)))
 
     def stats(self) -> dict:
         st = EngineStats()

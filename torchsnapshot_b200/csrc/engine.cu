@@ -23,7 +23,9 @@
 #include <fcntl.h>
 #include <string.h>
 #include <dirent.h>
+#include <sys/mman.h>
 #include <sys/resource.h>
+#include <sys/syscall.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -127,53 +129,88 @@ static std::vector<int> gpu_numa_cpus(int device) {
     return cpus;
 }
 
+// ---- host topology -------------------------------------------------------------------------------------------
+struct NumaNode {
+    int id;
+    std::vector<int> cpus;   // allowed hardware threads
+    std::vector<int> cores;  // first hardware thread of every allowed physical core
+};
+static std::vector<NumaNode> numa_nodes() {
+    cpu_set_t cur;
+    const bool have_aff = sched_getaffinity(0, sizeof(cur), &cur) == 0;
+    std::vector<NumaNode> out;
+    for (int node = 0; node < 64; ++node) {
+        std::string cl = read_small_file("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+        if (cl.empty()) {
+            if (node > 8) break;
+            continue;
+        }
+        NumaNode n;
+        n.id = node;
+        for (int c : parse_cpulist(cl)) {
+            if (have_aff && (c >= CPU_SETSIZE || !CPU_ISSET(c, &cur))) continue;
+            n.cpus.push_back(c);
+            std::vector<int> sib = parse_cpulist(read_small_file("/sys/devices/system/cpu/cpu" + std::to_string(c) + "/topology/thread_siblings_list"));
+            if (sib.empty() || sib[0] == c) n.cores.push_back(c);
+        }
+        if (!n.cpus.empty()) out.push_back(n);
+    }
+    return out;
+}
+
 // Placement of the I/O workers (TSNAP_B200_IO_PIN):
 //   none   (default) leave it to the scheduler
 //   local  all workers on the CPUs of the GPU's NUMA node
-//   spread one physical core per worker, alternating between the NUMA nodes (page-cache copies are bound by
-//          per-node locks and memory channels: both sockets' worth helps), offset by LOCAL_RANK so that ranks
+//   node   workers split evenly over the NUMA nodes, each bound to its node's CPUs and serving that node's queue:
+//          with TSNAP_B200_RING_NUMA=interleave every page-cache copy reads a pinned slot of the worker's own node
+//   spread one physical core per worker, alternating between the NUMA nodes, offset by LOCAL_RANK so that ranks
 //          sharing a host do not pile onto the same cores
-static std::vector<std::vector<int>> io_worker_cpus(int n, const std::vector<int>& gpu_node_cpus) {
+static std::vector<WorkerSpec> io_worker_specs(int n, const std::vector<int>& gpu_node_cpus, const std::vector<int>& ring_nodes,
+                                               int* n_queues) {
     const char* env = getenv("TSNAP_B200_IO_PIN");
     std::string mode = env ? env : "none";
-    if (mode == "local") return {gpu_node_cpus};
-    if (mode != "spread") return {};
-    cpu_set_t cur;
-    const bool have_aff = sched_getaffinity(0, sizeof(cur), &cur) == 0;
-    std::vector<std::vector<int>> node_cores;  // per node: first hardware thread of every allowed physical core
-    for (int node = 0; node < 16; ++node) {
-        std::string cl = read_small_file("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
-        if (cl.empty()) break;
-        std::vector<int> cores;
-        for (int c : parse_cpulist(cl)) {
-            if (have_aff && (c >= CPU_SETSIZE || !CPU_ISSET(c, &cur))) continue;
-            std::vector<int> sib = parse_cpulist(read_small_file("/sys/devices/system/cpu/cpu" + std::to_string(c) + "/topology/thread_siblings_list"));
-            if (!sib.empty() && sib[0] != c) continue;
-            cores.push_back(c);
-        }
-        if (!cores.empty()) node_cores.push_back(cores);
+    std::vector<WorkerSpec> out(size_t(n), WorkerSpec{});
+    *n_queues = 1;
+    if (mode == "local") {
+        for (WorkerSpec& w : out) w.cpus = gpu_node_cpus;
+        return out;
     }
-    if (node_cores.empty()) return {};
+    if (mode != "spread" && mode != "node") return out;
+    const std::vector<NumaNode> nodes = numa_nodes();
+    if (nodes.empty()) return out;
+    // queue q serves ring_nodes[q] when the ring is placed, else node q
+    std::vector<const NumaNode*> qnode;
+    if (!ring_nodes.empty()) {
+        for (int id : ring_nodes)
+            for (const NumaNode& nd : nodes)
+                if (nd.id == id) qnode.push_back(&nd);
+    }
+    if (qnode.empty())
+        for (const NumaNode& nd : nodes) qnode.push_back(&nd);
+    *n_queues = int(qnode.size());
     const char* lr = getenv("LOCAL_RANK");
     const int rank = lr ? atoi(lr) : 0;
-    std::vector<std::vector<int>> out;
     for (int i = 0; i < n; ++i) {
         const int g = rank * n + i;  // global worker ordinal on this host
-        const std::vector<int>& cores = node_cores[size_t(g) % node_cores.size()];
-        out.push_back({cores[(size_t(g) / node_cores.size()) % cores.size()]});
+        const int q = i % int(qnode.size());
+        out[size_t(i)].queue = q;
+        const NumaNode& nd = *qnode[size_t(q)];
+        if (mode == "node" || nd.cores.empty()) out[size_t(i)].cpus = nd.cpus;
+        else out[size_t(i)].cpus = {nd.cores[(size_t(g) / qnode.size()) % nd.cores.size()]};
     }
     return out;
 }
 
 // ---- WorkerPool ---------------------------------------------------------------------------------------
 static thread_local int g_lane = 0;  // ordinal of the current I/O worker (trace lanes)
-WorkerPool::WorkerPool(int n, const std::vector<std::vector<int>>& cpus) {
-    for (int i = 0; i < n; ++i) {
-        std::vector<int> mine = cpus.empty() ? std::vector<int>() : cpus[size_t(i) % cpus.size()];
-        threads_.emplace_back([this, mine, i] {
-            g_lane = i;
-            bind_current_thread(mine);
-            run();
+WorkerPool::WorkerPool(const std::vector<WorkerSpec>& workers, int n_queues) {
+    q_.resize(size_t(std::max(1, n_queues)));
+    for (size_t i = 0; i < workers.size(); ++i) {
+        const WorkerSpec w = workers[i];
+        threads_.emplace_back([this, w, i] {
+            g_lane = int(i);
+            bind_current_thread(w.cpus);
+            run(w.queue);
         });
     }
 }
@@ -185,53 +222,111 @@ WorkerPool::~WorkerPool() {
     cv_.notify_all();
     for (auto& t : threads_) t.join();
 }
-void WorkerPool::post(std::function<void()> fn) {
+void WorkerPool::post(std::function<void()> fn, int queue) {
     {
         std::lock_guard<std::mutex> g(mu_);
-        q_.push_back(std::move(fn));
+        const size_t q = queue >= 0 ? size_t(queue) % q_.size() : (rr_++ % q_.size());
+        q_[q].push_back(std::move(fn));
     }
-    cv_.notify_one();
+    cv_.notify_all();
 }
-void WorkerPool::run() {
+void WorkerPool::run(int home) {
+    const size_t nq = q_.size();
     for (;;) {
         std::function<void()> fn;
         {
             std::unique_lock<std::mutex> g(mu_);
-            cv_.wait(g, [this] { return stop_ || !q_.empty(); });
-            if (q_.empty()) return;
-            fn = std::move(q_.front());
-            q_.pop_front();
+            size_t found = nq;
+            for (;;) {
+                // own node's queue first, then help the others out (a remote copy beats an idle worker)
+                for (size_t k = 0; k < nq; ++k) {
+                    const size_t q = (size_t(home) + k) % nq;
+                    if (!q_[q].empty()) {
+                        found = q;
+                        break;
+                    }
+                }
+                if (found < nq || stop_) break;
+                cv_.wait(g);
+            }
+            if (found == nq) return;
+            fn = std::move(q_[found].front());
+            q_[found].pop_front();
         }
         fn();
     }
 }
 
 // ---- SlotRing -------------------------------------------------------------------------------------------
-int SlotRing::init(size_t slot_bytes, int n, bool pinned, size_t slack) {
+// anonymous memory bound to one NUMA node, faulted in, then pinned for DMA
+static char* alloc_on_node(size_t len, int node, bool pin) {
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    unsigned long mask[4] = {0, 0, 0, 0};
+    mask[size_t(node) / (8 * sizeof(unsigned long))] |= 1UL << (size_t(node) % (8 * sizeof(unsigned long)));
+    const long rc = syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, mask, sizeof(mask) * 8 + 1, 0);
+    if (rc != 0) {
+        munmap(p, len);
+        return nullptr;
+    }
+    madvise(p, len, MADV_HUGEPAGE);
+    memset(p, 0, len);
+    if (pin && cudaHostRegister(p, len, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, len);
+        return nullptr;
+    }
+    return static_cast<char*>(p);
+}
+
+int SlotRing::init(size_t slot_bytes, int n, bool pinned, size_t slack, const std::vector<int>& nodes) {
     slot_bytes_ = slot_bytes;
     slack_ = slack;
     pinned_ = pinned;
     for (int i = 0; i < n; ++i) {
         void* p = nullptr;
-        if (pinned) {
+        size_t maplen = 0;
+        int queue = -1;
+        if (!nodes.empty()) {
+            const size_t len = (slot_bytes + slack + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+            p = alloc_on_node(len, nodes[size_t(i) % nodes.size()], pinned);
+            if (p) {
+                maplen = len;
+                queue = int(size_t(i) % nodes.size());
+            }
+        }
+        if (!p && pinned) {
             // cudaHostAlloc returns page-aligned memory: fit for O_DIRECT as it is
             cudaError_t e = cudaHostAlloc(&p, slot_bytes + slack, cudaHostAllocDefault);
             if (e != cudaSuccess) return set_err(TSNAP_ECUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
-        } else {
+        } else if (!p) {
             if (posix_memalign(&p, 4096, slot_bytes + slack) != 0) return set_err(TSNAP_ENOMEM, "posix_memalign failed");
         }
+        placed_.push_back(Placed{static_cast<char*>(p), maplen, queue});
         all_.push_back(static_cast<char*>(p));
         free_.push_back(static_cast<char*>(p));
     }
     return TSNAP_OK;
 }
 void SlotRing::destroy() {
-    for (char* p : all_) {
-        if (pinned_) cudaFreeHost(p);
-        else free(p);
+    for (const Placed& s : placed_) {
+        if (s.len) {
+            if (pinned_) cudaHostUnregister(s.p);
+            munmap(s.p, s.len);
+        } else if (pinned_) {
+            cudaFreeHost(s.p);
+        } else {
+            free(s.p);
+        }
     }
+    placed_.clear();
     all_.clear();
     free_.clear();
+}
+int SlotRing::queue_of(const char* p) const {
+    for (const Placed& s : placed_)
+        if (s.p == p) return s.queue;
+    return -1;
 }
 char* SlotRing::acquire() {
     std::unique_lock<std::mutex> g(mu_);
@@ -540,7 +635,7 @@ static int ensure_ring(tsnap_engine* eng) {
     size_t sb = eng->cfg.pinned_slot_bytes ? eng->cfg.pinned_slot_bytes : (32ull << 20);
     sb = align_up(sb, 4096);
     const int n = eng->cfg.pinned_slots ? eng->cfg.pinned_slots : 32;
-    return eng->ring.init(sb, n, eng->has_device, 8192);
+    return eng->ring.init(sb, n, eng->has_device, 8192, eng->ring_nodes);
 }
 
 // Decides, per device file, between staging in the arena (pack/scatter kernels) and the direct link path, and
@@ -805,6 +900,11 @@ static void account_parts(tsnap_job* job, int64_t async_parts) {
     job->accounted = true;
 }
 
+// chunk I/O goes to the queue of the NUMA node the pinned slot lives on (node-affine workers, see io_worker_specs)
+static void post_slot(tsnap_engine* eng, char* slot, std::function<void()> fn) {
+    eng->io->post(std::move(fn), eng->ring.queue_of(slot));
+}
+
 // payload memcpys of chunk [lo, lo+n) of a direct file: one per dense run that intersects it
 static bool direct_chunk_copies(tsnap_job* job, const FileSpec& f, char* slot, uint64_t lo, uint64_t n, bool to_host) {
     tsnap_engine* eng = job->eng;
@@ -969,7 +1069,7 @@ static int run_save_inner(tsnap_job* job) {
                     job->last_copy_done_ms = t1;
                 }
                 auto tq = clk::now();
-                eng->io->post([eng, job, fp, fidx, slot, lo, n, tq] {
+                post_slot(eng, slot, [eng, job, fp, fidx, slot, lo, n, tq] {
                     job->io_queue_us += int64_t(ms_since(tq) * 1000.0);
                     NvtxRange nvtx_w("tsnap:pwrite chunk");
                     if (!dbg_skip_write && !job->failed() && ensure_open(job, *fp, true)) {
@@ -1084,7 +1184,7 @@ static int run_load_inner(tsnap_job* job) {
             for (uint64_t lo = 0; lo < f->nbytes; lo += sb) {
                 const uint64_t n = std::min(sb, f->nbytes - lo);
                 char* slot = eng->ring.acquire();
-                eng->io->post([eng, job, w, wi, f, fi, base, slot, lo, n, shared, last_wave] {
+                post_slot(eng, slot, [eng, job, w, wi, f, fi, base, slot, lo, n, shared, last_wave] {
                     NvtxRange nvtx_r("tsnap:pread chunk + H2D enqueue");
                     cudaSetDevice(eng->device);
                     bool ok = !job->failed();
@@ -1398,10 +1498,27 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
         eng->completion_thread = std::thread(completion_main, eng);
     }
     {
+        // TSNAP_B200_RING_NUMA: none (default) | gpu (all slots on the GPU's node) | interleave (slot i on node i % nodes)
+        const char* rn = getenv("TSNAP_B200_RING_NUMA");
+        const std::string ring_mode = rn ? rn : "none";
+        if (ring_mode == "interleave") {
+            for (const NumaNode& nd : numa_nodes()) eng->ring_nodes.push_back(nd.id);
+        } else if (ring_mode == "gpu" && cfg->device >= 0) {
+            char bus[32] = {0};
+            if (cudaDeviceGetPCIBusId(bus, sizeof(bus), cfg->device) == cudaSuccess) {
+                std::string id(bus);
+                for (char& c : id) c = char(tolower(c));
+                const std::string node = read_small_file("/sys/bus/pci/devices/" + id + "/numa_node");
+                if (!node.empty() && atoi(node.c_str()) >= 0) eng->ring_nodes.push_back(atoi(node.c_str()));
+            }
+        }
         const int nio = cfg->io_threads > 0 ? cfg->io_threads : 16;
-        std::vector<std::vector<int>> placement = io_worker_cpus(nio, eng->numa_cpus);
-        if (placement.empty() && !eng->numa_cpus.empty()) placement.push_back(eng->numa_cpus);  // TSNAP_B200_NUMA=1
-        eng->io = new WorkerPool(nio, placement);
+        int nq = 1;
+        std::vector<WorkerSpec> specs = io_worker_specs(nio, eng->numa_cpus.empty() ? std::vector<int>() : eng->numa_cpus, eng->ring_nodes, &nq);
+        if (!eng->numa_cpus.empty())
+            for (WorkerSpec& w : specs)
+                if (w.cpus.empty()) w.cpus = eng->numa_cpus;  // TSNAP_B200_NUMA=1
+        eng->io = new WorkerPool(specs, nq);
     }
     eng->drain_thread = std::thread(drain_main, eng);
     *out = eng;
@@ -1979,6 +2096,44 @@ int tsnap_consume(tsnap_engine* eng, const void* host_buf, uint64_t nbytes, cons
     tsnap_job_destroy(job);
     if (rc != TSNAP_OK) return set_err(rc, msg);
     return TSNAP_OK;
+}
+
+int tsnap_scatter_device(tsnap_engine* eng, const void* device_wire, uint64_t nbytes, const tsnap_copy_desc* members,
+                         int32_t n, void* consumer_stream) {
+    if (!eng || (nbytes && !device_wire) || (n > 0 && !members)) return set_err(TSNAP_EINVAL, "null argument");
+    if (n == 0 || nbytes == 0) return TSNAP_OK;
+    if (!eng->has_device) return set_err(TSNAP_ECUDA, "device members on a host-only engine");
+    cudaSetDevice(eng->device);
+    // a job that is never queued: it only carries the planner state of one wave whose "arena" is the caller's buffer
+    tsnap_job job;
+    job.eng = eng;
+    job.kind = kLoad;
+    job.arena = static_cast<char*>(const_cast<void*>(device_wire));
+    job.arena_bytes = nbytes;
+    job.files.emplace_back();
+    FileSpec& f = job.files.back();
+    f.path = "<device wire>";
+    f.nbytes = nbytes;
+    for (int32_t i = 0; i < n; ++i) {
+        if (members[i].src_space != TSNAP_SPACE_WIRE || members[i].dst_space != TSNAP_SPACE_DEVICE)
+            return set_err(TSNAP_EINVAL, "scatter_device members go from WIRE to DEVICE");
+        int rc = add_member(&job, 0, &members[i], false);
+        if (rc != TSNAP_OK) return rc;
+    }
+    Wave w;
+    w.files.push_back(0);
+    int rc = plan_wave(&job, w);
+    if (rc != TSNAP_OK) return rc;
+    cudaEvent_t ev = eng->get_event();
+    cudaError_t e = cudaEventRecord(ev, static_cast<cudaStream_t>(consumer_stream));
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(eng->s_kernel, ev, 0);
+    eng->put_event(ev);
+    if (e != cudaSuccess) return set_err(TSNAP_ECUDA, std::string("scatter_device: ") + cudaGetErrorString(e));
+    rc = launch_wave(&job, w);
+    if (rc == TSNAP_OK && cudaEventSynchronize(w.ev_done) != cudaSuccess) rc = set_err(TSNAP_ECUDA, "scatter kernel failed");
+    for (cudaEvent_t x : {w.ev_k0, w.ev_k1, w.ev_kr, w.ev_k2, w.ev_done})
+        if (x) cudaEventDestroy(x);
+    return rc;
 }
 
 // ---- planning introspection + host execution -----------------------------------------------------------------

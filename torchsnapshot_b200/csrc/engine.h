@@ -20,18 +20,27 @@ namespace tsnap {
 int set_err(int code, const std::string& msg);
 const char* last_err();
 
+// where one I/O worker runs: CPU set it is bound to (empty = unbound) and the queue it serves first
+struct WorkerSpec {
+    std::vector<int> cpus;
+    int queue = 0;
+};
+
 class WorkerPool {
    public:
-    // cpus[i % cpus.size()] = CPU set worker i is bound to (empty vector / empty set = unbound)
-    WorkerPool(int n, const std::vector<std::vector<int>>& cpus);
+    // one queue per NUMA node when the workers are node-bound (else one queue): a task posted with the queue of the
+    // node its pinned slot lives on is copied by a CPU of that node; an idle worker takes work from the other queues
+    WorkerPool(const std::vector<WorkerSpec>& workers, int n_queues);
     ~WorkerPool();
-    void post(std::function<void()> fn);
+    void post(std::function<void()> fn, int queue = -1);
     int size() const { return int(threads_.size()); }
+    int queues() const { return int(q_.size()); }
 
    private:
-    void run();
+    void run(int home);
     std::vector<std::thread> threads_;
-    std::deque<std::function<void()>> q_;
+    std::vector<std::deque<std::function<void()>>> q_;
+    size_t rr_ = 0;
     std::mutex mu_;
     std::condition_variable cv_;
     bool stop_ = false;
@@ -40,11 +49,13 @@ class WorkerPool {
 // fixed-size pinned slots handed out to in-flight chunks
 class SlotRing {
    public:
-    // every slot has `slack` extra bytes of capacity behind slot_bytes (O_DIRECT reads are widened to 4 KiB blocks)
-    int init(size_t slot_bytes, int n, bool pinned, size_t slack);
+    // every slot has `slack` extra bytes of capacity behind slot_bytes (O_DIRECT reads are widened to 4 KiB blocks).
+    // `nodes` non-empty: slot i is placed on NUMA node nodes[i % size] (mmap + mbind + cudaHostRegister)
+    int init(size_t slot_bytes, int n, bool pinned, size_t slack, const std::vector<int>& nodes);
     void destroy();
     char* acquire();  // blocks
     void release(char* p);
+    int queue_of(const char* p) const;  // index into `nodes` of the slot's NUMA node, -1 when unplaced
     size_t slot_bytes() const { return slot_bytes_; }
     size_t total_bytes() const { return (slot_bytes_ + slack_) * all_.size(); }
     int count() const { return int(all_.size()); }
@@ -52,6 +63,12 @@ class SlotRing {
    private:
     size_t slot_bytes_ = 0, slack_ = 0;
     bool pinned_ = false;
+    struct Placed {
+        char* p;
+        size_t len;   // mapping length when the slot was mmap'ed + registered (0: cudaHostAlloc / posix_memalign)
+        int queue;
+    };
+    std::vector<Placed> placed_;
     std::vector<char*> all_;
     std::vector<char*> free_;
     std::mutex mu_;
@@ -72,6 +89,7 @@ struct tsnap_engine {
     bool odirect = false;    // TSNAP_ENGINE_ODIRECT
     bool no_arena = false;   // TSNAP_ENGINE_NO_ARENA
     std::vector<int> numa_cpus;  // CPUs of the NUMA node the GPU hangs off (empty = no binding)
+    std::vector<int> ring_nodes; // NUMA nodes the ring slots are placed on, in queue order (empty = wherever they land)
     cudaStream_t s_kernel = nullptr;  // pack / unpack kernels
     cudaStream_t s_copy = nullptr;    // D2H / H2D payload copies
     tsnap::SlotRing ring;

@@ -252,13 +252,131 @@ def sync_execute_write_reqs(
     return event_loop.run_until_complete(execute_write_reqs(write_reqs, storage, memory_budget_bytes, rank))
 
 
-async def execute_read_reqs(read_reqs: List[ReadReq], storage: StoragePlugin, memory_budget_bytes: int, rank: int) -> None:
+# ---- read-once restore of replicated state over NVLink --------------------------------------------------------------
+_READ_ONCE_MIN_BYTES = 4 << 20
+_READ_ONCE_BUF_BYTES = 256 << 20
+
+
+def _plan_shared_reads(pg: PGWrapper, mine: Dict[Tuple[str, int, int], int]) -> Dict[Tuple[str, int, int], int]:
+    """{(path, lo, hi): reader rank} for the byte ranges EVERY rank of `pg` is about to read into GPU tensors — DDP /
+    replicated state, which the reference reads from storage once per rank (T:manifest_ops.py:69-85).  One object
+    all-gather; the greedy least-loaded assignment is evaluated identically on every rank."""
+    world = pg.get_world_size()
+    gathered: List[Optional[List[Tuple[str, int, int]]]] = [None] * world
+    pg.all_gather_object(gathered, sorted(mine))
+    common = set(gathered[0] or [])
+    for g in gathered[1:]:
+        common &= set(g or [])
+    if sum(hi - lo for _, lo, hi in common) < _READ_ONCE_MIN_BYTES:
+        return {}
+    load = [0] * world
+    owner: Dict[Tuple[str, int, int], int] = {}
+    for key in sorted(common, key=lambda k: (-(k[2] - k[1]), k)):
+        r = min(range(world), key=lambda i: (load[i], i))
+        owner[key] = r
+        load[r] += key[2] - key[1]
+    return owner
+
+
+def _read_once_eligible(pg: Optional[PGWrapper]) -> bool:
+    import torch.distributed as dist
+
+    if pg is None or pg.pg is None or pg.get_world_size() < 2 or os.environ.get("TSNAP_B200_READ_ONCE", "1") == "0":
+        return False
+    try:
+        if dist.get_backend(pg.pg) != "nccl":
+            return False
+    except Exception:
+        return False
+    # peers exchange the file images GPU to GPU: only worth it (and only NVLink) inside one host
+    return get_local_world_size(pg) == pg.get_world_size()
+
+
+def _shift_descs(descs, delta: int):
+    out = []
+    for d in descs:
+        c = _native.CopyDesc.from_buffer_copy(d)
+        c.src_addr = d.src_addr + delta
+        out.append(c)
+    return out
+
+
+def _execute_shared_reads(pg: PGWrapper, root: str, shared: List[Tuple[Tuple[str, int, int], list, list]], owner: Dict[Tuple[str, int, int], int]) -> int:
+    """Every shared byte range is read from storage by its owner only (file -> pinned ring -> H2D straight into a
+    staging tensor), broadcast GPU-to-GPU, and scattered into the live tensors by every rank's scatter kernels.
+    Returns the bytes this rank read from storage."""
+    import torch.distributed as dist
+
+    rank, world = pg.get_rank(), pg.get_world_size()
+    dev = torch.cuda.current_device()
+    eng = _native.get_engine(dev)
+    by_key = {k: (descs, keep) for k, descs, keep in shared}
+    # identical on every rank: per owner, ranges packed into buffers of <= _READ_ONCE_BUF_BYTES (256 B-aligned members)
+    plan: List[Tuple[int, int, List[Tuple[Tuple[str, int, int], int]]]] = []  # (owner, nbytes, [(key, offset)])
+    for r in range(world):
+        cur: List[Tuple[Tuple[str, int, int], int]] = []
+        off = 0
+        for key in sorted(k for k, o in owner.items() if o == r):
+            n = key[2] - key[1]
+            if cur and off + n > _READ_ONCE_BUF_BYTES:
+                plan.append((r, off, cur))
+                cur, off = [], 0
+            cur.append((key, off))
+            off += (n + 255) // 256 * 256
+        if cur:
+            plan.append((r, off, cur))
+    # my own buffers are filled first, all in one engine job (reads of all ranks proceed concurrently)
+    mine = {i: torch.empty(nb, dtype=torch.uint8, device=f"cuda:{dev}") for i, (r, nb, _) in enumerate(plan) if r == rank}
+    job = None
+    read_bytes = 0
+    if mine:
+        job = eng.load_job()
+        for i, buf in mine.items():
+            for key, off in plan[i][2]:
+                path, lo, hi = key
+                fi = job.add_file(os.path.join(root, path), hi - lo, offset=lo)
+                job.add_member(fi, _native.load_desc(buf[off : off + (hi - lo)], 0), buf)
+                read_bytes += hi - lo
+        job.submit(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        waited = False
+        for i, (r, nb, members) in enumerate(plan):
+            if r == rank:
+                if not waited:
+                    job.wait()
+                    waited = True
+                buf = mine[i]
+            else:
+                buf = torch.empty(nb, dtype=torch.uint8, device=f"cuda:{dev}")
+            dist.broadcast(buf, src=dist.get_global_rank(pg.pg, r), group=pg.pg)
+            descs = []
+            for key, off in members:
+                descs += _shift_descs(by_key[key][0], off)
+            # ordered after the broadcast on the current stream; synchronous, so `buf` may be dropped afterwards
+            eng.scatter_device(buf, descs, stream=torch.cuda.current_stream(dev).cuda_stream)
+            mine.pop(i, None)
+    finally:
+        if job is not None:
+            job.destroy()
+    return read_bytes
+
+
+async def execute_read_reqs(
+    read_reqs: List[ReadReq], storage: StoragePlugin, memory_budget_bytes: int, rank: int, shared_pg: Optional[PGWrapper] = None
+) -> None:
+    """`shared_pg`: set by Snapshot.restore (a collective call on that group): byte ranges that every rank reads into
+    GPU tensors are then read from storage once and exchanged over NVLink (see _execute_shared_reads)."""
     begin = time.monotonic()
     loop = asyncio.get_running_loop()
     root = _native_root(storage, "read")
     native: Optional[_NativeJobs] = None
     generic: List[ReadReq] = []
     total = 0
+    # every rank of the group takes part in the negotiation, also one with nothing to share (storage the engine does
+    # not drive, CPU-only targets): the all-gather is a collective
+    read_once = _read_once_eligible(shared_pg)
+    candidates: List[Tuple[Tuple[str, int, int], list, list]] = []
+    described_reqs = []
     for rr in read_reqs:
         described = describe_consumer(rr.buffer_consumer) if root is not None else None
         if described is not None:
@@ -269,19 +387,46 @@ async def execute_read_reqs(read_reqs: List[ReadReq], storage: StoragePlugin, me
                 lo, hi = 0, wire_nbytes
             if not descs:
                 continue
-            if native is None:
-                native = _NativeJobs(save=False)
-            job = native.job_for(_engine_key(keep))
-            fi = job.add_file(os.path.join(root, rr.path), hi - lo, offset=lo)
-            for d in descs:
-                job.add_member(fi, d)
-            job._keepalive.extend(keep)
-            total += hi - lo
+            described_reqs.append((rr, descs, keep, lo, hi))
         else:
             generic.append(rr)
+    owner: Dict[Tuple[str, int, int], int] = {}
+    if read_once:
+        mine = {}
+        for rr, descs, keep, lo, hi in described_reqs:
+            if hi > lo and all(d.dst_space == _native.SPACE_DEVICE for d in descs) and (rr.path, lo, hi) not in mine:
+                mine[(rr.path, lo, hi)] = hi - lo
+        owner = _plan_shared_reads(shared_pg, mine)
+    seen_shared = set()
+    for rr, descs, keep, lo, hi in described_reqs:
+        key = (rr.path, lo, hi)
+        if key in owner and all(d.dst_space == _native.SPACE_DEVICE for d in descs):
+            if key in seen_shared:  # two consumers of the same range: both scatter from the one image
+                for c in candidates:
+                    if c[0] == key:
+                        c[1].extend(descs)
+                        c[2].extend(keep)
+            else:
+                seen_shared.add(key)
+                candidates.append((key, list(descs), list(keep)))
+            total += hi - lo
+            continue
+        if native is None:
+            native = _NativeJobs(save=False)
+        job = native.job_for(_engine_key(keep))
+        fi = job.add_file(os.path.join(root, rr.path), hi - lo, offset=lo)
+        for d in descs:
+            job.add_member(fi, d)
+        job._keepalive.extend(keep)
+        total += hi - lo
     try:
         if native is not None:
             native.submit()
+        if candidates:
+            LAST_STATS["read_once"] = {"ranges": len(candidates), "bytes": sum(k[2] - k[1] for k, _, _ in candidates),
+                                       "bytes_read_by_this_rank": _execute_shared_reads(shared_pg, root, candidates, owner)}
+        else:
+            LAST_STATS["read_once"] = None
         if generic:
             executor = ThreadPoolExecutor(max_workers=_MAX_PER_RANK_CPU_CONCURRENCY)
             io_slots = asyncio.Semaphore(get_max_per_rank_io_concurrency())
@@ -326,6 +471,7 @@ async def execute_read_reqs(read_reqs: List[ReadReq], storage: StoragePlugin, me
 
 
 def sync_execute_read_reqs(
-    read_reqs: List[ReadReq], storage: StoragePlugin, memory_budget_bytes: int, rank: int, event_loop: asyncio.AbstractEventLoop
+    read_reqs: List[ReadReq], storage: StoragePlugin, memory_budget_bytes: int, rank: int, event_loop: asyncio.AbstractEventLoop,
+    shared_pg: Optional[PGWrapper] = None,
 ) -> None:
-    event_loop.run_until_complete(execute_read_reqs(read_reqs, storage, memory_budget_bytes, rank))
+    event_loop.run_until_complete(execute_read_reqs(read_reqs, storage, memory_budget_bytes, rank, shared_pg))

@@ -231,13 +231,19 @@ class Snapshot:
         self, key: str, stateful: Optional[Stateful], strict: bool, storage: StoragePlugin, pgw: PGWrapper, loop: asyncio.AbstractEventLoop
     ) -> None:
         if stateful is None:
+            # the other ranks negotiate read-once ranges for this key (one all-gather): take part with nothing to share
+            from .scheduler import _plan_shared_reads, _read_once_eligible
+
+            if _read_once_eligible(pgw):
+                _plan_shared_reads(pgw, {})
             return
         manifest, merged = get_manifest_for_rank(self.metadata, pgw.get_rank())
         # load straight into the tensors the stateful already owns (no second copy of the state)
         _, flat = flatten(stateful.state_dict(), prefix=key)
         targets = {k: v for k, v in flat.items() if isinstance(v, (torch.Tensor, ShardedTensor, DTensor))}
         handle_sharded_tensor_elasticity(manifest, merged, list(targets.keys()))
-        state_dict = self._get_state_dict_for_manifest(key, manifest, targets, pgw, storage, loop)
+        # restore is collective on pgw: replicated ranges may be read once and exchanged GPU to GPU
+        state_dict = self._get_state_dict_for_manifest(key, manifest, targets, pgw, storage, loop, shared_pg=pgw)
         if isinstance(stateful, torch.nn.Module):
             stateful.load_state_dict(state_dict, strict=strict)
         else:
@@ -252,6 +258,7 @@ class Snapshot:
         storage: StoragePlugin,
         loop: asyncio.AbstractEventLoop,
         replicate_from_rank0: bool = False,
+        shared_pg: Optional[PGWrapper] = None,
     ) -> Any:
         from .flatten import _encode
 
@@ -271,7 +278,7 @@ class Snapshot:
         if not is_batching_disabled():
             read_reqs = batch_read_requests(read_reqs)
         budget = get_process_memory_budget_bytes(pgw)
-        sync_execute_read_reqs(read_reqs, storage, budget, 0 if replicate_from_rank0 else pgw.get_rank(), loop)
+        sync_execute_read_reqs(read_reqs, storage, budget, 0 if replicate_from_rank0 else pgw.get_rank(), loop, shared_pg)
         return inflate(containers, {k: f.obj for k, f in futs.items()}, prefix=key)
 
     def get_state_dict_for_key(self, key: str, replicate_from_rank0: bool = False) -> Any:
