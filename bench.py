@@ -378,7 +378,9 @@ def run_c3(ctx: Ctx, T, impl_desc: str) -> None:
     }
     line["steps_ms"] = [round(x, 2) for x in step_ms]
     line["take_blocking_ms"] = {"async_take_returns_ms": mean(block_ms), "async_total_ms": mean(async_total_ms), "sync_take_ms": take_ms,
-                                "engine_device_done_ms": blocking_stats.get("device_done_ms")}
+                                "engine_device_done_ms": blocking_stats.get("device_done_ms"), "async_take_returns_ms_each": [round(x, 2) for x in block_ms],
+                                "phases_of_last_async_take_ms": {k: round(v, 2) for k, v in ((S.LAST_STATS.get("take_phases_ms") or {}) if ours else {}).items()},
+                                "write_phases_of_last_async_take_ms": {k: round(v, 2) for k, v in ((S.LAST_STATS.get("write_phases_ms") or {}) if ours else {}).items()}}
     line["restore"] = {"value": payload_total / 1e9 / (mean(restore_ms) / 1e3), "unit": "GB/s", "ms": mean(restore_ms), "verified_all_tensors_all_ranks": ok,
                        "scatter_kernel_ms": load_stats.get("kernel_ms")}
     line["clocks"] = clocks
@@ -659,6 +661,7 @@ def run_c4(ctx: Ctx, T, impl_desc: str) -> None:
     line["train_step_ms"] = base_ms
     line["step_ms_during_drain"] = mean(r["steps_ms_total"] for r in res) / during
     line["overlap_pct"] = round(100 * overlap, 1) if overlap is not None else None
+    line["training_time_lost_per_snapshot_ms"] = blocked + extra  # blocked inside async_take + slow-down of the steps that overlap the drain
     line["overlap_definition"] = "1 - (extra time the training steps took while the snapshot drained) / (time from async_take returning until the snapshot was complete)"
     line["background_ms"] = drain
     line["sync_take_ms"] = sync_ms

@@ -49,7 +49,17 @@ for mode in ("sync", "async"):
     d2(torch.randn(8, 1024, device=dev)).sum().backward(); o2.step()
     t2 = ShardedTensor._init_from_local_shards([Shard(tensor=torch.zeros(64, 96, device=dev), metadata=ShardMetadata(shard_offsets=[rank * 64, 0], shard_sizes=[64, 96], placement=f"rank:{rank}/cuda:{local}"))], (rows, 96))
     e2 = B.StateDict(rank_tag="", noise=torch.zeros(1000, device=dev), table=t2)
+    eng = B.get_engine(local)
+    r0 = eng.stats()["bytes_read"]
     B.Snapshot(path).restore({"model": d2, "optim": o2, "extra": e2})
+    # read-once restore: replicated ranges (model + optimizer, ~19 MB) are read from storage by ONE rank each and
+    # travel GPU to GPU; per-rank and sharded state is read by its owner.  Sum over ranks ~= bytes on disk, not world x.
+    read = torch.tensor([eng.stats()["bytes_read"] - r0], dtype=torch.float64, device=dev)
+    dist.all_reduce(read)
+    on_disk = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(path) for f in fs if f != ".snapshot_metadata")
+    assert read.item() <= 1.25 * on_disk, (read.item(), on_disk, "replicated files were re-read by several ranks")
+    if rank == 0:
+        print(f"{mode}: restore read {int(read.item())} bytes from storage over {world} ranks for {on_disk} bytes on disk", flush=True)
     for (k, a), (_, b) in zip(ddp.state_dict().items(), d2.state_dict().items()): assert torch.equal(a, b), k
     s1, s2 = opt.state_dict()["state"], o2.state_dict()["state"]
     for k in s1:

@@ -666,10 +666,13 @@ def get_engine(device: int = -1, **kwargs) -> Engine:
         eng = _engines.get(key)
         if eng is None:
             env = os.environ
-            # the kernel's buffered-write path on the measured hosts peaks at ~16 concurrent writers per box
-            # and degrades beyond (profiles/r01_host_write_probe.json), so ranks sharing a host split them
+            # the kernel's buffered-write path on the measured hosts peaks at ~16 concurrent writers per box and
+            # degrades beyond (profiles/r01_host_write_probe.json).  Ranks sharing a host therefore draw every chunk
+            # I/O from one host-wide pool of 16 tokens (engine.cu: HostTokens); each rank keeps 16 workers so that a
+            # rank draining alone can use the whole pool.  TSNAP_B200_HOST_IO_TOKENS=0 restores the static split.
             local_world = max(1, int(env.get("LOCAL_WORLD_SIZE", "1")))
-            default_io = max(2, 16 // local_world)
+            tokens = int(env.get("TSNAP_B200_HOST_IO_TOKENS", "16" if local_world > 1 else "0"))
+            default_io = 16 if (tokens > 0 or local_world == 1) else max(2, 16 // local_world)
             opts = dict(
                 io_threads=int(env.get("TSNAP_B200_IO_THREADS", str(default_io))),
                 pinned_slot_bytes=int(env.get("TSNAP_B200_PINNED_SLOT_BYTES", "0")),

@@ -23,8 +23,10 @@
 #include <fcntl.h>
 #include <string.h>
 #include <dirent.h>
+#include <sys/ipc.h>
 #include <sys/mman.h>
 #include <sys/resource.h>
+#include <sys/sem.h>
 #include <sys/syscall.h>
 #include <sys/stat.h>
 #include <sys/types.h>
@@ -128,6 +130,64 @@ static std::vector<int> gpu_numa_cpus(int device) {
     }
     return cpus;
 }
+
+// ---- host-wide I/O tokens -----------------------------------------------------------------------------------
+// The kernel's buffered-write path peaks at ~16 concurrent writers per HOST and degrades beyond
+// (profiles/r01_host_write_probe.json), so the engines of all ranks on a host draw every chunk I/O from one pool of
+// tokens (a SysV semaphore: SEM_UNDO gives a killed process's tokens back).  A rank that drains alone — the last one
+// of a take, a restore on fewer ranks than the save — gets the whole pool instead of a static 1/N share.
+// TSNAP_B200_HOST_IO_TOKENS: pool size, 0 = off (default: off for one rank per host, 16 otherwise; see engine_create).
+struct HostTokens {
+    int semid = -1;
+    void init(int tokens) {
+        if (tokens <= 0) return;
+        // one semaphore per (uid, pool size): engines configured with different pool sizes do not share a counter
+        const key_t key = key_t(0x74530000 | ((tokens & 0xff) << 8) | (getuid() & 0xff));
+        int id = semget(key, 1, IPC_CREAT | IPC_EXCL | 0600);
+        if (id >= 0) {
+            union semun_ {
+                int val;
+                struct semid_ds* buf;
+                unsigned short* array;
+            } arg;
+            arg.val = tokens;
+            if (semctl(id, 0, SETVAL, arg) != 0) return;
+        } else {
+            id = semget(key, 1, 0600);
+            if (id < 0) return;
+            // the creator may not have initialised it yet: sem_otime stays 0 until the first semop
+            for (int i = 0; i < 100; ++i) {
+                struct semid_ds ds;
+                union semun_ {
+                    int val;
+                    struct semid_ds* buf;
+                    unsigned short* array;
+                } arg;
+                arg.buf = &ds;
+                if (semctl(id, 0, IPC_STAT, arg) == 0 && (ds.sem_otime != 0 || semctl(id, 0, GETVAL) > 0)) break;
+                usleep(1000);
+            }
+        }
+        semid = id;
+    }
+    void acquire() {
+        if (semid < 0) return;
+        struct sembuf op = {0, -1, SEM_UNDO};
+        while (semop(semid, &op, 1) != 0 && errno == EINTR) {
+        }
+    }
+    void release() {
+        if (semid < 0) return;
+        struct sembuf op = {0, 1, SEM_UNDO};
+        while (semop(semid, &op, 1) != 0 && errno == EINTR) {
+        }
+    }
+};
+static HostTokens g_tokens;
+struct TokenGuard {
+    TokenGuard() { g_tokens.acquire(); }
+    ~TokenGuard() { g_tokens.release(); }
+};
 
 // ---- host topology -------------------------------------------------------------------------------------------
 struct NumaNode {
@@ -1075,7 +1135,10 @@ static int run_save_inner(tsnap_job* job) {
                     if (!dbg_skip_write && !job->failed() && ensure_open(job, *fp, true)) {
                         auto tb = clk::now();
                         const double t0w = eng->trace ? job->now_ms() : 0;
-                        if (write_chunk(*fp, slot, n, lo) != 0) job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
+                        {
+                            TokenGuard tok;
+                            if (write_chunk(*fp, slot, n, lo) != 0) job->fail(TSNAP_EIO, "pwrite " + fp->path + ": " + strerror(errno));
+                        }
                         job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
                         if (eng->trace) job->add_trace(TSNAP_TR_PWRITE, g_lane, fidx, t0w, job->now_ms(), n);
                     }
@@ -1196,9 +1259,12 @@ static int run_load_inner(tsnap_job* job) {
                         auto tb = clk::now();
                         if (!ensure_open(job, *f, false)) {
                             ok = false;
-                        } else if (read_chunk(*f, slot, n, f->offset + lo, &skip) != 0) {
-                            job->fail(TSNAP_EIO, "pread " + f->path + ": " + strerror(errno));
-                            ok = false;
+                        } else {
+                            TokenGuard tok;
+                            if (read_chunk(*f, slot, n, f->offset + lo, &skip) != 0) {
+                                job->fail(TSNAP_EIO, "pread " + f->path + ": " + strerror(errno));
+                                ok = false;
+                            }
                         }
                         job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
                     }
@@ -1496,6 +1562,15 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
         const char* keep = getenv("TSNAP_B200_KEEP_ARENA");
         eng->keep_arena = keep && keep[0] == '1';
         eng->completion_thread = std::thread(completion_main, eng);
+    }
+    {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            const char* t = getenv("TSNAP_B200_HOST_IO_TOKENS");
+            const char* lw = getenv("LOCAL_WORLD_SIZE");
+            const int local_world = lw ? atoi(lw) : 1;
+            g_tokens.init(t ? atoi(t) : (local_world > 1 ? 16 : 0));
+        });
     }
     {
         // TSNAP_B200_RING_NUMA: none (default) | gpu (all slots on the GPU's node) | interleave (slot i on node i % nodes)
@@ -1929,7 +2004,11 @@ int tsnap_engine_probe(tsnap_engine* eng, int kind, const char* dir, uint64_t by
             const uint64_t fi = c % nfiles, k = c / nfiles;
             char* slot = eng->ring.acquire();
             eng->io->post([&, fi, k, slot, write] {
-                int r = write ? pwrite_all(fds[fi], slot, sb, k * sb) : pread_all(fds[fi], slot, sb, k * sb);
+                int r;
+                {
+                    TokenGuard tok;
+                    r = write ? pwrite_all(fds[fi], slot, sb, k * sb) : pread_all(fds[fi], slot, sb, k * sb);
+                }
                 if (r != 0) err.store(errno ? errno : EIO);
                 eng->ring.release(slot);
                 if (left.fetch_sub(1) == 1) {
