@@ -50,7 +50,13 @@ enum tsnap_dtype {
     TSNAP_F32 = 7,
     TSNAP_F64 = 8,
     TSNAP_BOOL = 9,
-    TSNAP_DTYPE_COUNT = 10
+    /* 1-byte affine-quantized wire elements (torch.qint8 / torch.quint8 int_repr).  Only as the WIRE side of a save
+     * from a floating-point source: q = clamp(round(x / q_scale) + q_zero_point) computed in the pack kernel, followed
+     * by the 16-byte trailer of the reference's per-tensor format [q_scale: double][q_zero_point: int64]
+     * (T:serialization.py:278-310) — the north star's "quantize in the pack kernel". */
+    TSNAP_QINT8 = 10,
+    TSNAP_QUINT8 = 11,
+    TSNAP_DTYPE_COUNT = 12
 };
 
 /* where a side of a copy lives */
@@ -88,6 +94,8 @@ typedef struct tsnap_copy_desc {
     int32_t src_space;  /* enum tsnap_space */
     int32_t dst_space;  /* enum tsnap_space */
     int32_t reserved;
+    double q_scale;        /* dst_dtype TSNAP_QINT8 / TSNAP_QUINT8 only */
+    int64_t q_zero_point;
 } tsnap_copy_desc;
 
 typedef struct tsnap_engine tsnap_engine;

@@ -28,7 +28,7 @@ def test_abi_version_and_dtype_sizes():
 
 def test_struct_layouts_match_header():
     # sizes the C side assumes (checked indirectly: a wrong layout breaks every parity test, this localises it)
-    assert ctypes.sizeof(_native.CopyDesc) == 8 + 8 + 3 * 8 * 8 + 6 * 4
+    assert ctypes.sizeof(_native.CopyDesc) == 8 + 8 + 3 * 8 * 8 + 6 * 4 + 8 + 8
     assert ctypes.sizeof(_native.EngineConfig) == 32
     assert ctypes.sizeof(_native.TraceRec) == 40
     assert ctypes.sizeof(_native.ArenaHint) == 32

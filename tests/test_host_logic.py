@@ -163,3 +163,39 @@ def test_cast_on_save_is_fused_and_matches_torch(tmp_path):
                       h=torch.zeros(7).half(), d=torch.zeros(5, dtype=torch.float64))
     snap.restore({"m": tgt})
     assert torch.equal(tgt["w"], st["w"].bfloat16()) and torch.equal(tgt["wt"], st["wt"].bfloat16()) and torch.equal(tgt["d"], st["d"])
+
+
+def test_quantize_on_save_matches_torch_and_the_reference_format(tmp_path):
+    """quantize_on_save: payload == int_repr bytes of torch.quantize_per_tensor + [scale: double][zero_point: int64]
+    (the reference's per-tensor format, T:serialization.py:278-310; its own codec reads it back), restoring into the
+    float tensors dequantises."""
+    import struct
+    import sys
+
+    import torch
+
+    import torchsnapshot_b200 as B
+    from torchsnapshot_b200.serialization import per_tensor_qtensor_from_bytes
+
+    torch.manual_seed(0)
+    st = {"w": torch.randn(1000, 33), "wt": torch.randn(64, 48).t(), "h": torch.randn(77).bfloat16(), "u": torch.rand(501) * 3 - 1, "i": torch.arange(10)}
+    for qdt in (torch.qint8, torch.quint8):
+        path = str(tmp_path / f"s_{qdt}".replace(".", "_"))
+        snap = B.Snapshot.take(path, {"m": B.StateDict(**st)}, _custom_tensor_prepare_func=B.quantize_on_save(qdt, only="m/[whu]*"))
+        man = snap.get_manifest()
+        assert man["0/m/i"].serializer == "buffer_protocol" and man["0/m/w"].serializer == "per_tensor_qtensor"
+        hook = B.quantize_on_save(qdt)
+        for k in ("w", "wt", "h", "u"):
+            data = open(f"{path}/{man[f'0/m/{k}'].location}", "rb").read()
+            _, scale, zp = hook.tsnap_quant(f"m/{k}", st[k])
+            q = torch.quantize_per_tensor(st[k].float().contiguous(), scale, zp, qdt)
+            want = q.int_repr().numpy().tobytes() + struct.pack("d", q.q_scale()) + struct.pack("q", q.q_zero_point())
+            assert data == want, (qdt, k)
+            back = per_tensor_qtensor_from_bytes(data, qdt, list(st[k].shape))
+            assert torch.equal(back.int_repr(), q.int_repr()) and back.q_scale() == q.q_scale()
+        tgt = B.StateDict(w=torch.zeros(1000, 33), wt=torch.zeros(48, 64), h=torch.zeros(77).bfloat16(), u=torch.zeros(501), i=torch.zeros(10, dtype=torch.long))
+        snap.restore({"m": tgt})
+        assert torch.equal(tgt["i"], st["i"])
+        for k in ("w", "wt", "u"):
+            _, scale, _ = hook.tsnap_quant(f"m/{k}", st[k])
+            assert (tgt[k] - st[k]).abs().max().item() <= scale * 0.5 + 1e-6, k

@@ -375,3 +375,40 @@ def test_timeline_shows_the_pipeline_overlapping(tmp_path, fresh_engines):
     d = str(tmp_path / "probe")
     os.makedirs(d)
     assert eng.probe(N.PROBE_WRITE, 1 << 29, d) > 0.1 and eng.probe(N.PROBE_READ, 1 << 29, d) > 0.1
+
+
+# ---- cast / quantize fused into the pack kernel, through the public API ----------------------------------------------
+def test_cast_and_quantize_on_save_on_gpu(tmp_path):
+    import struct
+
+    torch.manual_seed(1)
+    w = torch.randn(2048, 1031, device=DEV)
+    st = {"w": w, "wt": torch.randn(300, 200, device=DEV).t(), "h": torch.randn(4099, device=DEV).half(), "i": torch.arange(100, device=DEV)}
+    # cast: payload == tensor.to(bf16) computed by torch on the same device, no processed tensor materialised
+    eng = B.get_engine(0)
+    k0 = eng.stats()["kernels_launched"]
+    snap = B.Snapshot.take(str(tmp_path / "c"), {"m": B.StateDict(**st)}, _custom_tensor_prepare_func=B.cast_on_save(torch.bfloat16, only="m/w*"))
+    assert eng.stats()["kernels_launched"] > k0
+    man = snap.get_manifest()
+    for k in ("w", "wt"):
+        assert man[f"0/m/{k}"].dtype == "torch.bfloat16"
+        assert open(tmp_path / "c" / man[f"0/m/{k}"].location, "rb").read() == wire_bytes(st[k].to(torch.bfloat16)), k
+    assert man["0/m/h"].dtype == "torch.float16"
+    # quantize: int_repr of torch.quantize_per_tensor on the same device + the reference's 16-byte trailer
+    for qdt in (torch.qint8, torch.quint8):
+        hook = B.quantize_on_save(qdt, only="m/[wh]*")
+        path = tmp_path / f"q{qdt}".replace(".", "_")
+        snap = B.Snapshot.take(str(path), {"m": B.StateDict(**st)}, _custom_tensor_prepare_func=hook)
+        man = snap.get_manifest()
+        for k in ("w", "wt", "h"):
+            _, scale, zp = hook.tsnap_quant(f"m/{k}", st[k])
+            q = torch.quantize_per_tensor(st[k].float().contiguous(), scale, zp, qdt)
+            want = bytes(q.int_repr().cpu().numpy().tobytes()) + struct.pack("d", q.q_scale()) + struct.pack("q", q.q_zero_point())
+            got = open(path / man[f"0/m/{k}"].location, "rb").read()
+            assert len(got) == len(want)
+            ndiff = sum(a != b for a, b in zip(got, want))
+            assert ndiff == 0, (qdt, k, ndiff)
+        tgt = B.StateDict(w=torch.zeros_like(w), wt=torch.zeros(200, 300, device=DEV), h=torch.zeros(4099, device=DEV).half(), i=torch.zeros(100, dtype=torch.long, device=DEV))
+        snap.restore({"m": tgt})
+        _, scale, _ = hook.tsnap_quant("m/w", w)
+        assert (tgt["w"] - w).abs().max().item() <= scale * 0.5 + 1e-6 and torch.equal(tgt["i"], st["i"])

@@ -4,9 +4,9 @@ run as hand-written sm_100a kernels plus a native pinned-memory copy/I-O engine 
 the on-disk format is the reference's, byte for byte."""
 from ._native import NativeError, get_engine
 from .integration import install, uninstall
-from .prepare import cast_on_save
+from .prepare import cast_on_save, quantize_on_save
 from .snapshot import PendingSnapshot, Snapshot
 from .stateful import AppState, RNGState, StateDict, Stateful
 
 __version__ = "0.1.0"
-__all__ = ["Snapshot", "PendingSnapshot", "Stateful", "StateDict", "RNGState", "AppState", "NativeError", "get_engine", "install", "uninstall", "cast_on_save", "__version__"]
+__all__ = ["Snapshot", "PendingSnapshot", "Stateful", "StateDict", "RNGState", "AppState", "NativeError", "get_engine", "install", "uninstall", "cast_on_save", "quantize_on_save", "__version__"]

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtsnap_b200.so")
 MAX_DIMS = 8
 
 # enum tsnap_dtype
-U8, I8, I16, I32, I64, F16, BF16, F32, F64, BOOL = range(10)
+U8, I8, I16, I32, I64, F16, BF16, F32, F64, BOOL, QINT8, QUINT8 = range(12)
 # enum tsnap_space
 SPACE_DEVICE, SPACE_HOST, SPACE_WIRE = 0, 1, 2
 
@@ -66,6 +66,8 @@ class CopyDesc(C.Structure):
         ("src_space", C.c_int32),
         ("dst_space", C.c_int32),
         ("reserved", C.c_int32),
+        ("q_scale", C.c_double),
+        ("q_zero_point", C.c_int64),
     ]
 
 
@@ -315,8 +317,13 @@ def needs_contiguous_copy(t: torch.Tensor) -> bool:
     return len(sizes) > MAX_DIMS
 
 
-def save_desc(t: torch.Tensor, wire_offset: int, wire_dtype: Optional[torch.dtype] = None) -> CopyDesc:
-    """tensor view -> wire image at ``wire_offset`` (C-contiguous layout of ``t.shape``)."""
+_QUANT = {torch.qint8: QINT8, torch.quint8: QUINT8}
+
+
+def save_desc(t: torch.Tensor, wire_offset: int, wire_dtype: Optional[torch.dtype] = None, qparams: Optional[Tuple[float, int]] = None) -> CopyDesc:
+    """tensor view -> wire image at ``wire_offset`` (C-contiguous layout of ``t.shape``).  ``wire_dtype`` fuses a float
+    cast; with ``wire_dtype`` torch.qint8/quint8 and ``qparams=(scale, zero_point)`` the pack kernel quantises and
+    appends the 16-byte per-tensor trailer (T:serialization.py:278-310)."""
     d = CopyDesc()
     sizes, strides = list(t.shape), list(t.stride())
     if len(sizes) > MAX_DIMS:
@@ -331,7 +338,13 @@ def save_desc(t: torch.Tensor, wire_offset: int, wire_dtype: Optional[torch.dtyp
     d.src_addr = t.data_ptr()
     d.dst_addr = wire_offset
     d.src_dtype = tsnap_dtype(t.dtype)
-    d.dst_dtype = tsnap_dtype(wire_dtype or t.dtype)
+    if wire_dtype in _QUANT:
+        if qparams is None:
+            raise NativeError(-1, "quantising descriptors need qparams=(scale, zero_point)")
+        d.dst_dtype = _QUANT[wire_dtype]
+        d.q_scale, d.q_zero_point = float(qparams[0]), int(qparams[1])
+    else:
+        d.dst_dtype = tsnap_dtype(wire_dtype or t.dtype)
     d.src_space = _space_of(t)
     d.dst_space = SPACE_WIRE
     return d

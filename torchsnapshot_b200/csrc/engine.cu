@@ -1716,7 +1716,8 @@ static int add_member(tsnap_job* job, int32_t fi, const tsnap_copy_desc* d, bool
     uint64_t numel = 1;
     for (int i = 0; i < d->ndim; ++i) numel *= uint64_t(d->sizes[i]);
     if (save) {
-        const uint64_t end = d->dst_addr + numel * dtype_size(d->dst_dtype);
+        const bool quant = d->dst_dtype == TSNAP_QINT8 || d->dst_dtype == TSNAP_QUINT8;
+        const uint64_t end = d->dst_addr + numel * dtype_size(d->dst_dtype) + (quant && numel ? 16 : 0);
         if (end > f.nbytes) return set_err(TSNAP_EINVAL, "member exceeds the file's wire image");
     } else if (numel) {
         // furthest byte touched on the wire side

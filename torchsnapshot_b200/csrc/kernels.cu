@@ -684,6 +684,15 @@ __device__ __forceinline__ void store_bytes(char* p, const void* v, int n, bool 
         for (int i = 0; i < n; ++i) p[i] = c[i];
     }
 }
+// affine quantisation as torch's CUDA quantize_per_tensor does it: nearbyint(x / scale) + zero_point in double
+// precision, clamped to the integer range (ATen/native/quantized/cuda/AffineQuantizer.cu)
+__device__ __forceinline__ uint8_t quantize_elem(float x, double scale, int64_t zp, bool is_signed) {
+    long long q = (long long)(nearbyint((double)x / scale) + (double)zp);
+    const long long lo = is_signed ? -128 : 0, hi = is_signed ? 127 : 255;
+    q = q < lo ? lo : (q > hi ? hi : q);
+    return (uint8_t)(int8_t)q;
+}
+
 __device__ __forceinline__ void convert_store(char* p, uint32_t ddt, const char* sp, uint32_t sdt, bool aligned) {
     // <=32-bit float sources convert through fp32 (exact widening), fp64 sources narrow directly:
     // the same single rounding step torch's copy kernel performs.
@@ -771,6 +780,23 @@ __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
             }
             e0 += n & ~uint64_t(7);  // the ragged tail (< 8 elements) goes through the scalar loop below
         }
+    }
+    if (m.dst_dtype == TSNAP_QINT8 || m.dst_dtype == TSNAP_QUINT8) {
+        // quantise-on-save: 1-byte destination elements, consecutive threads write consecutive bytes
+        const bool is_signed = m.dst_dtype == TSNAP_QINT8;
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += kLsuThreads) {
+            const uint64_t row = e / m.inner, col = e - row * m.inner;
+            int64_t so, dofs;
+            outer_offsets(m, row, &so, &dofs);
+            const float x = (float)load_elem(sb + so + col * m.src_esz, m.src_dtype);
+            reinterpret_cast<uint8_t*>(db + dofs)[col] = quantize_elem(x, m.q_scale, m.q_zero_point, is_signed);
+        }
+        if ((m.shift & 1) && hi == m.bytes && threadIdx.x < 16) {
+            // the per-tensor trailer of T:serialization.py:278-310, byte by byte (the payload length is arbitrary)
+            const unsigned char* t = threadIdx.x < 8 ? reinterpret_cast<const unsigned char*>(&m.q_scale) : reinterpret_cast<const unsigned char*>(&m.q_zero_point);
+            db[m.bytes + threadIdx.x] = (char)t[threadIdx.x & 7];
+        }
+        return;
     }
     bool aligned = (m.dst % m.dst_esz) == 0;
     for (uint32_t i = 0; i < m.nouter; ++i) aligned = aligned && ((uint64_t)m.dstride[i] % m.dst_esz) == 0;

@@ -6,7 +6,7 @@
 
 namespace tsnap {
 
-static const size_t kDtypeSize[TSNAP_DTYPE_COUNT] = {1, 1, 2, 4, 8, 2, 2, 4, 8, 1};
+static const size_t kDtypeSize[TSNAP_DTYPE_COUNT] = {1, 1, 2, 4, 8, 2, 2, 4, 8, 1, 1, 1};
 
 size_t dtype_size(int dt) {
     if (dt < 0 || dt >= TSNAP_DTYPE_COUNT) return 0;
@@ -15,9 +15,11 @@ size_t dtype_size(int dt) {
 
 static bool is_float(int dt) { return dt == TSNAP_F16 || dt == TSNAP_BF16 || dt == TSNAP_F32 || dt == TSNAP_F64; }
 
+static bool is_quant(int dt) { return dt == TSNAP_QINT8 || dt == TSNAP_QUINT8; }
+
 bool cast_supported(int s, int d) {
-    if (s == d) return true;
-    return is_float(s) && is_float(d);
+    if (s == d) return !is_quant(s);  // quantised wire elements only exist as the product of a quantising save
+    return is_float(s) && (is_float(d) || is_quant(d));
 }
 
 static inline uint64_t lowbit(uint64_t x) { return x & (~x + 1); }
@@ -60,8 +62,11 @@ int normalize_copy(const tsnap_copy_desc& d, uint64_t wire_base, bool allow_bulk
     if (d.src_space == TSNAP_SPACE_WIRE && d.dst_space == TSNAP_SPACE_WIRE)
         return fail(TSNAP_EINVAL, "wire-to-wire copies are not a thing");
     const bool cast = d.src_dtype != d.dst_dtype;
-    if (cast && !cast_supported(d.src_dtype, d.dst_dtype))
+    if (!cast_supported(d.src_dtype, d.dst_dtype))
         return fail(TSNAP_EUNSUP, "unsupported dtype conversion");
+    const bool quant = is_quant(d.dst_dtype);
+    if (quant && (d.dst_space != TSNAP_SPACE_WIRE || !(d.q_scale > 0)))
+        return fail(TSNAP_EINVAL, "quantising copies need a WIRE destination and q_scale > 0");
 
     // logical shape; C-contiguous element strides for a WIRE destination
     int64_t cstride[TSNAP_MAX_DIMS];
@@ -112,6 +117,11 @@ int normalize_copy(const tsnap_copy_desc& d, uint64_t wire_base, bool allow_bulk
     if (cast) {
         m.mode = kModeCast;
         m.unit = uint32_t(ed);
+        if (quant) {
+            m.q_scale = d.q_scale;
+            m.q_zero_point = d.q_zero_point;
+            m.shift = 1;  // append [scale][zero_point] behind the payload
+        }
         if (nd > 0 && dims[nd - 1].ss == int64_t(es) && dims[nd - 1].ds == int64_t(ed)) {
             m.inner = uint64_t(dims[nd - 1].size);
             --nd;
@@ -243,6 +253,15 @@ static inline double load_as_double(const void* p, uint32_t dt) {
         default: { double x; std::memcpy(&x, p, 8); return x; }
     }
 }
+// torch's CPU quantize_val (non-FBGEMM build, c10::qint8/quint8): zero_point + nearbyint(value * (1.0f / scale))
+static inline uint8_t quantize_host(float x, double scale, int64_t zp, bool is_signed) {
+    const float inv = 1.0f / float(scale);
+    int64_t q = zp + int64_t(std::nearbyint(x * inv));
+    const int64_t lo = is_signed ? -128 : 0, hi = is_signed ? 127 : 255;
+    q = q < lo ? lo : (q > hi ? hi : q);
+    return uint8_t(int8_t(q));
+}
+
 static inline void store_from(void* p, uint32_t dt, const void* sp, uint32_t sdt) {
     // convert through float when the source is <= 32 bit (exact), through double otherwise
     if (sdt == TSNAP_F64) {
@@ -302,11 +321,21 @@ void host_copy_range(const Member& m, uint64_t lo, uint64_t hi) {
     }
     // cast: lo/hi are dst bytes, multiples of the dst element size by construction
     const uint64_t e0 = lo / m.dst_esz, e1 = hi / m.dst_esz;
+    const bool quant = m.dst_dtype == TSNAP_QINT8 || m.dst_dtype == TSNAP_QUINT8;
     for (uint64_t e = e0; e < e1; ++e) {
         const uint64_t row = e / m.inner, col = e % m.inner;
         int64_t so, dofs;
         outer_offsets(m, row, &so, &dofs);
-        store_from(dst + dofs + col * m.dst_esz, m.dst_dtype, src + so + col * m.src_esz, m.src_dtype);
+        if (quant) {
+            const float x = float(load_as_double(src + so + col * m.src_esz, m.src_dtype));
+            reinterpret_cast<uint8_t*>(dst + dofs)[col] = quantize_host(x, m.q_scale, m.q_zero_point, m.dst_dtype == TSNAP_QINT8);
+        } else {
+            store_from(dst + dofs + col * m.dst_esz, m.dst_dtype, src + so + col * m.src_esz, m.src_dtype);
+        }
+    }
+    if (quant && (m.shift & 1) && hi == m.bytes) {
+        std::memcpy(dst + m.bytes, &m.q_scale, 8);
+        std::memcpy(dst + m.bytes + 8, &m.q_zero_point, 8);
     }
 }
 

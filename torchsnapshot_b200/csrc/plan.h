@@ -53,6 +53,8 @@ struct alignas(16) Member {
     int64_t osize[kMaxOuter];
     int64_t sstride[kMaxOuter];  // bytes
     int64_t dstride[kMaxOuter];  // bytes
+    double q_scale;              // kModeCast to TSNAP_QINT8/QUINT8: affine quantisation parameters; when `shift` bit 0
+    int64_t q_zero_point;        // is set the tile holding the last element appends the 16-byte trailer at dst + bytes
 };
 
 struct Tile {

@@ -34,6 +34,8 @@ from ..serialization import (
 
 RAW = Serializer.BUFFER_PROTOCOL.value
 PICKLED = Serializer.TORCH_SAVE.value
+from ..prepare import PER_TENSOR_QTENSOR, fused_quant_of  # noqa: E402
+from ..serialization import per_tensor_qtensor_from_bytes  # noqa: E402
 PrepareFunc = Callable[[torch.Tensor, bool], torch.Tensor]
 
 
@@ -41,6 +43,8 @@ def entry_nbytes(entry: TensorEntry) -> int:
     n = dtype_to_element_size(string_to_dtype(entry.dtype))
     for s in entry.shape:
         n *= s
+    if entry.serializer == PER_TENSOR_QTENSOR:
+        n += 16  # [q_scale: double][q_zero_point: int64] behind the int_repr bytes (T:serialization.py:278-310)
     return n
 
 
@@ -66,6 +70,8 @@ class TensorBufferStager(BufferStager):
         self.entry = entry
         self.is_async_snapshot = is_async_snapshot
         self._tensor_prepare_func = _tensor_prepare_func
+        # (qdtype, scale, zero_point) when the entry is a quantise-on-save one: the pack kernel quantises
+        self.qparams = fused_quant_of(_tensor_prepare_func, tensor) if entry.serializer == PER_TENSOR_QTENSOR else None
 
     # ---- engine-facing description ------------------------------------------------------------
     def is_raw(self) -> bool:
@@ -84,6 +90,12 @@ class TensorBufferStager(BufferStager):
         return entry_nbytes(self.entry)
 
     def native_descs(self, wire_offset: int) -> Tuple[List["_native.CopyDesc"], List[torch.Tensor]]:
+        if self.qparams is not None:
+            t = self.tensor.detach()
+            if self.is_async_snapshot and t.device.type == "cpu":
+                t = t.clone()
+            qdtype, scale, zp = self.qparams
+            return [_native.save_desc(t, wire_offset, wire_dtype=qdtype, qparams=(scale, zp))], [t]
         t = self.source()
         if t.numel() == 0:
             return [], []
@@ -97,7 +109,7 @@ class TensorBufferStager(BufferStager):
 
     # ---- asyncio seam ---------------------------------------------------------------------------
     async def stage_buffer(self, executor: Optional[Executor] = None) -> BufferType:
-        if not self.is_raw():
+        if not self.is_raw() and self.qparams is None:
             # complex / quantized tensors: unchanged torch.save path (out of scope of the engine)
             t = self.source()
             cpu = t.cpu() if t.device.type != "cpu" else t
@@ -145,6 +157,8 @@ class TensorBufferConsumer(BufferConsumer):
             return torch_load_from_bytes(buf)
         if entry.serializer == RAW:
             return tensor_from_memoryview(memoryview(buf), dtype=string_to_dtype(entry.dtype), shape=entry.shape)
+        if entry.serializer == PER_TENSOR_QTENSOR:
+            return per_tensor_qtensor_from_bytes(bytes(buf), string_to_dtype(entry.dtype), list(entry.shape))
         raise ValueError(f"Unrecognized serializer: {entry.serializer}.")
 
     async def consume_buffer(self, buf: bytes, executor: Optional[Executor] = None) -> None:
@@ -199,9 +213,12 @@ class TensorIOPreparer:
                 "_tensor_prepare_func shouldn't change the tensor's shape "
                 f"(changed from {tensor.shape} to {traced.shape})."
             )
+        serializer = RAW if traced.dtype in BUFFER_PROTOCOL_SUPPORTED_DTYPES else PICKLED
+        if _tensor_prepare_func is not None and fused_quant_of(_tensor_prepare_func, tensor) is not None:
+            serializer = PER_TENSOR_QTENSOR  # int_repr + 16-byte trailer, produced by the pack kernel
         entry = TensorEntry(
             location=storage_path,
-            serializer=RAW if traced.dtype in BUFFER_PROTOCOL_SUPPORTED_DTYPES else PICKLED,
+            serializer=serializer,
             dtype=dtype_to_string(traced.dtype),
             shape=list(traced.shape),
             replicated=False,
@@ -215,7 +232,11 @@ class TensorIOPreparer:
 
     @staticmethod
     def can_load_inplace(entry: Union[TensorEntry, ChunkedTensorEntry], obj: Any) -> bool:
-        return isinstance(obj, torch.Tensor) and string_to_dtype(entry.dtype) == obj.dtype and list(entry.shape) == list(obj.shape)
+        if not isinstance(obj, torch.Tensor) or list(entry.shape) != list(obj.shape):
+            return False
+        if getattr(entry, "serializer", None) == PER_TENSOR_QTENSOR and obj.dtype in _FLOATS:
+            return True  # dequantised into the float tensor it was quantised from (tensor_copy)
+        return string_to_dtype(entry.dtype) == obj.dtype
 
     @staticmethod
     def empty_tensor_from_entry(entry: Union[TensorEntry, ChunkedTensorEntry]) -> torch.Tensor:

@@ -36,6 +36,10 @@ def _castable(src: torch.dtype, dst: torch.dtype) -> bool:
 def _describe_tensor_stager(st: Any, offset: int) -> Optional[Described]:
     entry = getattr(st, "entry", None)
     tensor = getattr(st, "tensor", None)
+    if entry is not None and isinstance(tensor, torch.Tensor) and getattr(st, "qparams", None) is not None:
+        # quantise-on-save: the pack kernel produces int_repr + trailer (prepare.quantize_on_save)
+        descs, keep = st.native_descs(offset)
+        return descs, keep, tensor.numel() + 16
     if entry is None or not isinstance(tensor, torch.Tensor) or getattr(entry, "serializer", None) != RAW:
         return None
     if entry.dtype not in _DTYPES:
