@@ -439,7 +439,8 @@ class Job:
         total, largest = hint["total_bytes"], hint["largest_file_bytes"]
         if total == 0:
             return
-        if self.engine.flags & ENGINE_NO_ARENA:
+        no_dense_staging = bool(self.engine.flags & ENGINE_NO_ARENA)
+        if no_dense_staging and hint["strided_total_bytes"] == 0:
             self.set_arena(None)
             return
         cap = self.engine.hbm_staging_bytes
@@ -451,7 +452,9 @@ class Job:
             if cap:
                 allowed = min(allowed, cap)
             cands = []
-            if total <= allowed:
+            if no_dense_staging:
+                pass  # only what the strided / converting members need (below)
+            elif total <= allowed:
                 cands.append(total)
             elif allowed >= 2 * largest:
                 cands.append(allowed)
@@ -683,6 +686,11 @@ def get_engine(device: int = -1, **kwargs) -> Engine:
             # degrades beyond (profiles/r01_host_write_probe.json).  Ranks sharing a host therefore draw every chunk
             # I/O from one host-wide pool of 16 tokens (engine.cu: HostTokens); each rank keeps 16 workers so that a
             # rank draining alone can use the whole pool.  TSNAP_B200_HOST_IO_TOKENS=0 restores the static split.
+            # Placement measured on the 2-socket B200 hosts (profiles/r02_sink_sweep.md): pinned ring interleaved over the
+            # NUMA nodes + workers bound to a node and serving that node's slots = every page-cache copy is node-local:
+            # take 35-44 -> 46-47.5 GB/s, restore 36-40 -> 44-49 GB/s at N=1.  The engine reads both from the environment.
+            env.setdefault("TSNAP_B200_RING_NUMA", "interleave")
+            env.setdefault("TSNAP_B200_IO_PIN", "node")
             local_world = max(1, int(env.get("LOCAL_WORLD_SIZE", "1")))
             tokens = int(env.get("TSNAP_B200_HOST_IO_TOKENS", "16" if local_world > 1 else "0"))
             default_io = 16 if (tokens > 0 or local_world == 1) else max(2, 16 // local_world)

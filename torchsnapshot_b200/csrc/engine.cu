@@ -219,16 +219,16 @@ static std::vector<NumaNode> numa_nodes() {
 }
 
 // Placement of the I/O workers (TSNAP_B200_IO_PIN):
-//   none   (default) leave it to the scheduler
+//   none   leave it to the scheduler
 //   local  all workers on the CPUs of the GPU's NUMA node
-//   node   workers split evenly over the NUMA nodes, each bound to its node's CPUs and serving that node's queue:
+//   node   (default) workers split evenly over the NUMA nodes, each bound to its node's CPUs and serving that node's queue:
 //          with TSNAP_B200_RING_NUMA=interleave every page-cache copy reads a pinned slot of the worker's own node
 //   spread one physical core per worker, alternating between the NUMA nodes, offset by LOCAL_RANK so that ranks
 //          sharing a host do not pile onto the same cores
 static std::vector<WorkerSpec> io_worker_specs(int n, const std::vector<int>& gpu_node_cpus, const std::vector<int>& ring_nodes,
                                                int* n_queues) {
     const char* env = getenv("TSNAP_B200_IO_PIN");
-    std::string mode = env ? env : "none";
+    std::string mode = env ? env : "node";
     std::vector<WorkerSpec> out(size_t(n), WorkerSpec{});
     *n_queues = 1;
     if (mode == "local") {
@@ -237,6 +237,7 @@ static std::vector<WorkerSpec> io_worker_specs(int n, const std::vector<int>& gp
     }
     if (mode != "spread" && mode != "node") return out;
     const std::vector<NumaNode> nodes = numa_nodes();
+    if (nodes.size() < 2 && mode == "node") return out;  // one node: nothing to be affine to
     if (nodes.empty()) return out;
     // queue q serves ring_nodes[q] when the ring is placed, else node q
     std::vector<const NumaNode*> qnode;
@@ -702,28 +703,31 @@ static int ensure_ring(tsnap_engine* eng) {
 // groups the staged files into waves that fit the arena.  job->waves = staged waves, then at most one direct wave.
 static int build_waves(tsnap_job* job) {
     tsnap_engine* eng = job->eng;
-    const ArenaNeed need = arena_need(job);
-    if (need.total == 0) return TSNAP_OK;
+    const ArenaNeed all = arena_need(job);
+    if (all.total == 0) return TSNAP_OK;
     if (!eng->has_device) return set_err(TSNAP_ECUDA, "job has device members but the engine is host-only");
+    // TSNAP_ENGINE_NO_ARENA: dense members never go through HBM staging; strided/converting ones still have to
+    ArenaNeed need = all;
     if (eng->no_arena) {
-        job->arena = nullptr;
-        job->arena_bytes = 0;
-    } else if (!job->arena_set) {
-        ensure_arena(eng, need);
+        need.total = all.nd_total;
+        need.largest = all.nd_largest;
+    }
+    if (!job->arena_set) {
+        if (need.total) ensure_arena(eng, need);
         job->arena = eng->arena;
         job->arena_bytes = eng->arena_bytes;
     }
     const uint64_t A = job->arena_bytes;
     bool stage_dense;
     uint64_t staged_total, staged_largest;
-    if (A >= need.total || (A >= 2 * need.largest && need.largest > 0)) {
+    if (!eng->no_arena && (A >= all.total || (A >= 2 * all.largest && all.largest > 0))) {
         stage_dense = true;
-        staged_total = need.total;
-        staged_largest = need.largest;
+        staged_total = all.total;
+        staged_largest = all.largest;
     } else {
         stage_dense = false;
-        staged_total = need.nd_total;
-        staged_largest = need.nd_largest;
+        staged_total = all.nd_total;
+        staged_largest = all.nd_largest;
         if (staged_total > A && 2 * staged_largest > A)
             return set_err(TSNAP_ECUDA, "not enough HBM staging for the strided/converting members: have " + std::to_string(A) +
                                             " bytes, need " + std::to_string(std::min(staged_total, 2 * staged_largest)));
@@ -1573,11 +1577,15 @@ int tsnap_engine_create(const tsnap_engine_config* cfg, tsnap_engine** out) {
         });
     }
     {
-        // TSNAP_B200_RING_NUMA: none (default) | gpu (all slots on the GPU's node) | interleave (slot i on node i % nodes)
+        // TSNAP_B200_RING_NUMA: interleave (default: slot i on node i % nodes) | gpu (all slots on the GPU's node) | none.
+        // With interleave + TSNAP_B200_IO_PIN=node (default) every page-cache copy reads a slot of the worker's own node
+        // and both sockets' memory channels and LRU locks share the load (profiles/r02_sink_sweep.md).
         const char* rn = getenv("TSNAP_B200_RING_NUMA");
-        const std::string ring_mode = rn ? rn : "none";
+        const std::string ring_mode = rn ? rn : "interleave";
         if (ring_mode == "interleave") {
-            for (const NumaNode& nd : numa_nodes()) eng->ring_nodes.push_back(nd.id);
+            const std::vector<NumaNode> nodes = numa_nodes();
+            if (nodes.size() >= 2)
+                for (const NumaNode& nd : nodes) eng->ring_nodes.push_back(nd.id);
         } else if (ring_mode == "gpu" && cfg->device >= 0) {
             char bus[32] = {0};
             if (cudaDeviceGetPCIBusId(bus, sizeof(bus), cfg->device) == cudaSuccess) {

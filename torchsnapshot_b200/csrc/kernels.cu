@@ -616,6 +616,29 @@ __device__ __noinline__ void tile_strided(const Member& m, uint32_t index) {
     }
 }
 
+// element i (compile-time constant after unrolling) of a 16 B vector, without taking the vector's address
+template <typename T>
+__device__ __forceinline__ T vec_get(const uint4& v, int i) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (sizeof(T) == 8) return (T)(((uint64_t)w[2 * i + 1] << 32) | w[2 * i]);
+    if (sizeof(T) == 4) return (T)w[i];
+    if (sizeof(T) == 2) return (T)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+    return (T)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+}
+template <typename T>
+__device__ __forceinline__ void vec_put(uint32_t (&w)[4], int i, T x) {
+    if (sizeof(T) == 8) {
+        w[2 * i] = (uint32_t)((uint64_t)x);
+        w[2 * i + 1] = (uint32_t)((uint64_t)x >> 32);
+    } else if (sizeof(T) == 4) {
+        w[i] = (uint32_t)x;
+    } else if (sizeof(T) == 2) {
+        w[i >> 1] |= (uint32_t)x << (16 * (i & 1));
+    } else {
+        w[i >> 2] |= (uint32_t)x << (8 * (i & 3));
+    }
+}
+
 // ---- tiled transpose ---------------------------------------------------------------------------
 // kModeTranspose: dim A is unit-stride on the source, dim B on the destination.  One tile = side x side elements of
 // (A, B) for one index of the remaining dims: read with consecutive threads along A, write with consecutive threads
@@ -641,19 +664,50 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
     const uint64_t a0 = (uint64_t)ia * kSide, b0 = (uint64_t)ib * kSide;
     const uint32_t na = (uint32_t)(sA - a0 < (uint64_t)kSide ? sA - a0 : kSide);
     const uint32_t nb = (uint32_t)(sB - b0 < (uint64_t)kSide ? sB - b0 : kSide);
-    const char* sp = reinterpret_cast<const char*>(m.src) + so + (int64_t)a0 * m.sstride[A] + (int64_t)b0 * m.sstride[B];
-    char* dp = reinterpret_cast<char*>(m.dst) + dofs + (int64_t)a0 * m.dstride[A] + (int64_t)b0 * m.dstride[B];
+    const int64_t ssB = m.sstride[B], dsA = m.dstride[A];
+    const char* sp = reinterpret_cast<const char*>(m.src) + so + (int64_t)a0 * m.sstride[A] + (int64_t)b0 * ssB;
+    char* dp = reinterpret_cast<char*>(m.dst) + dofs + (int64_t)a0 * dsA + (int64_t)b0 * m.dstride[B];
     T(*tile)[kSide + 1] = reinterpret_cast<T(*)[kSide + 1]>(tbuf);
+    constexpr int V = 16 / (int)sizeof(T);             // elements per 16 B vector
+    constexpr int kVecPerRow = kSide / V;
+    constexpr int kIter = kSide * kVecPerRow / kLsuThreads;
+    const bool full = na == (uint32_t)kSide && nb == (uint32_t)kSide && ((reinterpret_cast<uint64_t>(sp) | (uint64_t)ssB) & 15) == 0 &&
+                      ((reinterpret_cast<uint64_t>(dp) | (uint64_t)dsA) & 15) == 0;
+    if (full) {
+        // interior tile: 16 B vectors on both global sides, all loads in flight before the first shared-memory store
+        uint4 r[kIter];
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+            const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
+            r[k] = ld_stream16(sp + (int64_t)(idx / kVecPerRow) * ssB + (idx % kVecPerRow) * 16);
+        }
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+            const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
+            const uint32_t b = idx / kVecPerRow, v = idx % kVecPerRow;
+#pragma unroll
+            for (int i = 0; i < V; ++i) tile[b][v * V + i] = vec_get<T>(r[k], i);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+            const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
+            const uint32_t a = idx / kVecPerRow, v = idx % kVecPerRow;
+            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < V; ++i) vec_put<T>(w, i, tile[v * V + i][a]);
+            st_stream16(dp + (int64_t)a * dsA + v * 16, make_uint4(w[0], w[1], w[2], w[3]));
+        }
+        return;  // the caller's loop synchronises before the tile buffer is reused
+    }
+    // edge tiles / unaligned bases: element accesses, still coalesced on both sides
     constexpr int kRowsPerPass = kLsuThreads / kSide;
     const uint32_t tx = threadIdx.x % kSide, ty = threadIdx.x / kSide;
-    // read: tx runs along A (contiguous source), rows along B
     for (uint32_t b = ty; b < nb; b += kRowsPerPass)
-        if (tx < na) tile[b][tx] = __ldg(reinterpret_cast<const T*>(sp + (int64_t)b * m.sstride[B]) + tx);
+        if (tx < na) tile[b][tx] = __ldg(reinterpret_cast<const T*>(sp + (int64_t)b * ssB) + tx);
     __syncthreads();
-    // write: tx runs along B (contiguous destination), rows along A
     for (uint32_t a = ty; a < na; a += kRowsPerPass)
-        if (tx < nb) reinterpret_cast<T*>(dp + (int64_t)a * m.dstride[A])[tx] = tile[tx][a];
-    // the caller's loop synchronises before the tile buffer is reused
+        if (tx < nb) reinterpret_cast<T*>(dp + (int64_t)a * dsA)[tx] = tile[tx][a];
 }
 
 __device__ __noinline__ void tile_transpose(const Member& m, uint32_t index, unsigned char* tbuf) {
@@ -808,20 +862,26 @@ __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
     }
 }
 
-__global__ void __launch_bounds__(kLsuThreads, 3) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
-                                                                   const Tile* __restrict__ tiles, uint32_t ntiles) {
+// kMinBlocks = CTAs per SM the register allocation is bounded for: 3 caps it at 80 registers (the strided path then
+// spills), 2 at 128.  Both are built; TSNAP_B200_LSU_OCC picks (A/B in profiles/r02_kernel_cases.md).
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kLsuThreads, kMinBlocks) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
+                                                                            const Tile* __restrict__ tiles, uint32_t ntiles) {
     __shared__ Member sm;
     __shared__ __align__(16) unsigned char tbuf[64 * 65 * 8];  // transpose tile: 64 x 65 x 8 B >= 128 x 129 x 2 B
+    uint32_t loaded = 0xffffffffu;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const Tile tl = tiles[t];
-        // stage the member record in shared memory: every thread needs all of it
-        __syncthreads();
-        {
+        // stage the member record in shared memory: every thread needs all of it (consecutive tiles of a CTA mostly
+        // belong to the same member: reload only on change)
+        __syncthreads();  // also fences the previous tile's use of sm / tbuf
+        if (tl.member != loaded) {
             const uint32_t* g = reinterpret_cast<const uint32_t*>(members + tl.member);
             uint32_t* s = reinterpret_cast<uint32_t*>(&sm);
             for (uint32_t i = threadIdx.x; i < sizeof(Member) / 4; i += kLsuThreads) s[i] = g[i];
+            loaded = tl.member;
+            __syncthreads();
         }
-        __syncthreads();
         switch (sm.mode) {
             case kModeContig: tile_contig(sm, tl.index); break;
             case kModeStrided: tile_strided(sm, tl.index); break;
@@ -879,13 +939,17 @@ static void rows_launch(const Member* m, const Tile* t, uint32_t n, uint32_t gri
 
 // resident CTAs per SM of the LSU kernel, from the occupancy calculator: the persistent grid is exactly one wave
 static int g_lsu_ctas_per_sm = 3;
+static int g_lsu_occ = 2;
 
 cudaError_t init_kernels() {
     cudaError_t e = bulk_attr<3, 16384>();
     if (e == cudaSuccess) e = bulk_attr<2, 49152>();
     if (e == cudaSuccess) {
+        const char* occ = getenv("TSNAP_B200_LSU_OCC");
+        g_lsu_occ = occ && atoi(occ) == 3 ? 3 : 2;
         int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel, kLsuThreads, 0);
+        e = g_lsu_occ == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<3>, kLsuThreads, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<2>, kLsuThreads, 0);
         if (e == cudaSuccess && n > 0) g_lsu_ctas_per_sm = n;
     }
     return e;
@@ -918,7 +982,8 @@ cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t nt
     if (ntiles == 0) return cudaSuccess;
     uint32_t grid = (uint32_t)sm_count * (uint32_t)g_lsu_ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
-    tsnap_lsu_copy_kernel<<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
+    if (g_lsu_occ == 3) tsnap_lsu_copy_kernel<3><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
+    else tsnap_lsu_copy_kernel<2><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
     return cudaGetLastError();
 }
 
