@@ -58,6 +58,32 @@ def run(tag, env, do_async=False):
 
 MiB = 1 << 20
 base = {"TSNAP_B200_IO_THREADS": 16, "TSNAP_B200_PINNED_SLOTS": 64}
+if args.set == "trace":
+    # where do the occasional +50 ms takes come from?  12 traced takes, per-take landmarks of the engine timeline
+    for k in KEYS: os.environ.pop(k, None)
+    os.environ["TSNAP_B200_ENGINE_FLAGS"] = str(N.ENGINE_TRACE)
+    N.reset_engines()
+    B.Snapshot.take(os.path.join(root, "w"), app); shutil.rmtree(os.path.join(root, "w"))
+    for r in range(12):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        B.Snapshot.take(os.path.join(root, f"t{r}"), app)
+        torch.cuda.synchronize(); ms = (time.perf_counter() - t0) * 1e3
+        st = (S.LAST_STATS.get("save") or [{}])[0]
+        tr = (S.LAST_STATS.get("save_trace") or [[]])[0]
+        def span(kind):
+            rs = [x for x in tr if x["kind"] == kind]
+            return [round(min(x["t0_ms"] for x in rs), 1), round(max(x["t1_ms"] for x in rs), 1)] if rs else None
+        d2h = sorted((x for x in tr if x["kind"] == "d2h"), key=lambda x: x["t1_ms"])
+        print(json.dumps({"take_ms": round(ms, 1), "phases": {k: round(v, 1) for k, v in (S.LAST_STATS.get("take_phases_ms") or {}).items() if v > 0.5},
+                          "write_phases": {k: round(v, 1) for k, v in (S.LAST_STATS.get("write_phases_ms") or {}).items() if v > 0.5},
+                          "engine": {k: round(st.get(k, 0), 1) for k in ("plan_ms", "kernel_ms", "device_done_ms", "copy_ms", "total_ms", "slot_wait_ms")},
+                          "plan": span("plan"), "kernel": span("kernel"), "d2h": span("d2h"), "first_d2h_done": round(d2h[0]["t1_ms"], 1) if d2h else None,
+                          "pwrite": span("pwrite"), "open": span("open"),
+                          "slowest_d2h_gaps": sorted((round(b["t1_ms"] - a["t1_ms"], 1) for a, b in zip(d2h, d2h[1:])), reverse=True)[:3]}), flush=True)
+        shutil.rmtree(os.path.join(root, f"t{r}"))
+    shutil.rmtree(root, ignore_errors=True)
+    dist.destroy_process_group()
+    sys.exit(0)
 run("base t16 s64x32", base, do_async=True)
 if args.set in ("all", "threads"):
     for t in (8, 12, 20, 24, 32):

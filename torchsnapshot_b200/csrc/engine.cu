@@ -511,6 +511,30 @@ void tsnap_engine::put_event(cudaEvent_t e) {
     ev_free.push_back(e);
 }
 
+void* tsnap_engine::get_table(size_t bytes, size_t* cap) {
+    {
+        std::lock_guard<std::mutex> g(tbl_mu);
+        size_t best = SIZE_MAX;
+        for (size_t i = 0; i < tbl_free.size(); ++i)
+            if (tbl_free[i].first >= bytes && (best == SIZE_MAX || tbl_free[i].first < tbl_free[best].first)) best = i;
+        if (best != SIZE_MAX) {
+            auto kv = tbl_free[best];
+            tbl_free.erase(tbl_free.begin() + best);
+            *cap = kv.first;
+            return kv.second;
+        }
+    }
+    const size_t c = std::max<size_t>((bytes + (1u << 20) - 1) >> 20 << 20, 1u << 20);
+    void* p = nullptr;
+    if (cudaMalloc(&p, c) != cudaSuccess) return nullptr;
+    *cap = c;
+    return p;
+}
+void tsnap_engine::put_table(void* p, size_t cap) {
+    std::lock_guard<std::mutex> g(tbl_mu);
+    tbl_free.emplace_back(cap, p);
+}
+
 static void push_pending(tsnap_engine* eng, cudaEvent_t ev, std::function<void(bool)> fn) {
     {
         std::lock_guard<std::mutex> g(eng->c_mu);
@@ -554,7 +578,7 @@ static int plan_wave(tsnap_job* job, Wave& w) {
                 if (nt == 0) continue;
                 const uint32_t mi = uint32_t(w.members.size());
                 w.members.push_back(m);
-                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : w.tiles_lsu;
+                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : m.mode == kModeStrided ? w.tiles_strided : w.tiles_lsu;
                 (m.mode == kModeBulk ? job->stats.bytes_bulk : m.mode == kModeRows ? job->stats.bytes_rows : job->stats.bytes_lsu) += m.bytes;
                 for (uint64_t t = 0; t < nt; ++t) tv.push_back(Tile{mi, uint32_t(t)});
             }
@@ -562,7 +586,7 @@ static int plan_wave(tsnap_job* job, Wave& w) {
     }
     job->stats.n_tiles_bulk += w.tiles_bulk.size();
     job->stats.n_tiles_rows += w.tiles_rows.size();
-    job->stats.n_tiles_lsu += w.tiles_lsu.size();
+    job->stats.n_tiles_lsu += w.tiles_lsu.size() + w.tiles_strided.size();
     return TSNAP_OK;
 }
 
@@ -573,7 +597,8 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     const size_t bb = w.tiles_bulk.size() * sizeof(Tile);
     const size_t rb = w.tiles_rows.size() * sizeof(Tile);
     const size_t lb = w.tiles_lsu.size() * sizeof(Tile);
-    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256);
+    const size_t sb2 = w.tiles_strided.size() * sizeof(Tile);
+    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256);
     CUDA_TRY(cudaEventCreate(&w.ev_k0));
     CUDA_TRY(cudaEventCreate(&w.ev_k1));
     CUDA_TRY(cudaEventCreate(&w.ev_kr));
@@ -587,28 +612,31 @@ static int launch_wave(tsnap_job* job, Wave& w) {
         CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
         return TSNAP_OK;
     }
-    CUDA_TRY(cudaMallocAsync(&w.d_tables, w.table_bytes, eng->s_kernel));
+    w.d_tables = eng->get_table(w.table_bytes, &w.table_cap);  // returned to the pool when the job is destroyed
+    if (!w.d_tables) return set_err(TSNAP_ECUDA, "out of device memory for the launch tables");
     char* d = static_cast<char*>(w.d_tables);
     Member* d_members = reinterpret_cast<Member*>(d);
     Tile* d_bulk = reinterpret_cast<Tile*>(d + align_up(mb, 256));
     Tile* d_rows = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256));
     Tile* d_lsu = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256));
+    Tile* d_strided = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256));
     // pageable sources: the runtime stages them before returning, so the vectors may be freed later
     CUDA_TRY(cudaMemcpyAsync(d_members, w.members.data(), mb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (bb) CUDA_TRY(cudaMemcpyAsync(d_bulk, w.tiles_bulk.data(), bb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (rb) CUDA_TRY(cudaMemcpyAsync(d_rows, w.tiles_rows.data(), rb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (lb) CUDA_TRY(cudaMemcpyAsync(d_lsu, w.tiles_lsu.data(), lb, cudaMemcpyHostToDevice, eng->s_kernel));
-    job->stats.table_h2d_bytes += mb + bb + rb + lb;
+    if (sb2) CUDA_TRY(cudaMemcpyAsync(d_strided, w.tiles_strided.data(), sb2, cudaMemcpyHostToDevice, eng->s_kernel));
+    job->stats.table_h2d_bytes += mb + bb + rb + lb + sb2;
     CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
     CUDA_TRY(launch_bulk(d_members, d_bulk, uint32_t(w.tiles_bulk.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
     CUDA_TRY(launch_rows(d_members, d_rows, uint32_t(w.tiles_rows.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_kr, eng->s_kernel));
-    CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel));
+    CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel, false));
+    CUDA_TRY(launch_lsu(d_members, d_strided, uint32_t(w.tiles_strided.size()), eng->sm_count, eng->s_kernel, true));
     CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
-    CUDA_TRY(cudaFreeAsync(w.d_tables, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
-    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1);
+    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1) + (w.tiles_strided.empty() ? 0 : 1);
     job->stats.n_kernel_launches += nl;
     eng->kernels_launched += nl;
     return TSNAP_OK;
@@ -1648,6 +1676,7 @@ int tsnap_engine_destroy(tsnap_engine* eng) {
         cudaStreamSynchronize(eng->s_kernel);
         cudaStreamSynchronize(eng->s_copy);
         if (eng->arena) cudaFree(eng->arena);
+        for (auto& kv : eng->tbl_free) cudaFree(kv.second);
         for (cudaEvent_t e : eng->ev_free) cudaEventDestroy(e);
         cudaStreamDestroy(eng->s_kernel);
         cudaStreamDestroy(eng->s_copy);
@@ -1874,6 +1903,7 @@ int tsnap_job_destroy(tsnap_job* job) {
     }
     if (job->eng->has_device) cudaSetDevice(job->eng->device);
     for (Wave& w : job->waves) {
+        if (w.d_tables) job->eng->put_table(w.d_tables, w.table_cap);  // the job is done: its kernels have finished
         if (w.ev_k0) cudaEventDestroy(w.ev_k0);
         if (w.ev_k1) cudaEventDestroy(w.ev_k1);
         if (w.ev_kr) cudaEventDestroy(w.ev_kr);
@@ -2219,6 +2249,10 @@ int tsnap_scatter_device(tsnap_engine* eng, const void* device_wire, uint64_t nb
     if (e != cudaSuccess) return set_err(TSNAP_ECUDA, std::string("scatter_device: ") + cudaGetErrorString(e));
     rc = launch_wave(&job, w);
     if (rc == TSNAP_OK && cudaEventSynchronize(w.ev_done) != cudaSuccess) rc = set_err(TSNAP_ECUDA, "scatter kernel failed");
+    if (w.d_tables) {
+        if (rc != TSNAP_OK) cudaStreamSynchronize(eng->s_kernel);
+        eng->put_table(w.d_tables, w.table_cap);
+    }
     for (cudaEvent_t x : {w.ev_k0, w.ev_k1, w.ev_kr, w.ev_k2, w.ev_done})
         if (x) cudaEventDestroy(x);
     return rc;

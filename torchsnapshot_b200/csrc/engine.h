@@ -120,6 +120,11 @@ struct tsnap_engine {
     bool trim_arena = false;    // drain thread frees the HBM arena when it is idle
     bool busy = false;          // a job is being issued by the drain thread
     bool keep_arena = false;    // TSNAP_B200_KEEP_ARENA=1: do not give the engine-owned arena back when idle
+    // device buffers for the member/tile tables of a launch (grow-only pool: no allocator call on the launch path)
+    std::mutex tbl_mu;
+    std::vector<std::pair<size_t, void*>> tbl_free;
+    void* get_table(size_t bytes, size_t* cap);
+    void put_table(void* p, size_t cap);
     // event pool
     std::mutex ev_mu;
     std::vector<cudaEvent_t> ev_free;
@@ -166,9 +171,9 @@ struct Wave {
     uint64_t bytes = 0;       // arena bytes (256B-aligned file regions)
     uint64_t region_off = 0;  // offset of the region inside the arena
     std::vector<Member> members;
-    std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu;
+    std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu, tiles_strided;  // strided tiles run the 2-CTA/SM build of the LSU kernel
     void* d_tables = nullptr;
-    size_t table_bytes = 0;
+    size_t table_bytes = 0, table_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_kr = nullptr, ev_k2 = nullptr;  // kernel timing: bulk | rows | lsu
     bool timed = false;
     double kernel_ms = 0;

@@ -863,7 +863,8 @@ __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
 }
 
 // kMinBlocks = CTAs per SM the register allocation is bounded for: 3 caps it at 80 registers (the strided path then
-// spills), 2 at 128.  Both are built; TSNAP_B200_LSU_OCC picks (A/B in profiles/r02_kernel_cases.md).
+// spills), 2 at 128.  Both are built: strided tiles are launched on <2>, every other mode on <3> (kernels.h, A/B in
+// profiles/r02_kernel_cases.md).
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kLsuThreads, kMinBlocks) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
                                                                             const Tile* __restrict__ tiles, uint32_t ntiles) {
@@ -937,20 +938,17 @@ static void rows_launch(const Member* m, const Tile* t, uint32_t n, uint32_t gri
     tsnap_rows_copy_kernel<S, B><<<grid, 32, S * B + S * (int)sizeof(Member) + S * 8, st>>>(m, t, n);
 }
 
-// resident CTAs per SM of the LSU kernel, from the occupancy calculator: the persistent grid is exactly one wave
-static int g_lsu_ctas_per_sm = 3;
-static int g_lsu_occ = 2;
+// resident CTAs per SM of the two builds of the LSU kernel, from the occupancy calculator: each persistent grid is
+// exactly one wave
+static int g_lsu_ctas_per_sm[2] = {3, 2};
 
 cudaError_t init_kernels() {
     cudaError_t e = bulk_attr<3, 16384>();
     if (e == cudaSuccess) e = bulk_attr<2, 49152>();
     if (e == cudaSuccess) {
-        const char* occ = getenv("TSNAP_B200_LSU_OCC");
-        g_lsu_occ = occ && atoi(occ) == 3 ? 3 : 2;
         int n = 0;
-        e = g_lsu_occ == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<3>, kLsuThreads, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<2>, kLsuThreads, 0);
-        if (e == cudaSuccess && n > 0) g_lsu_ctas_per_sm = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<3>, kLsuThreads, 0) == cudaSuccess && n > 0) g_lsu_ctas_per_sm[0] = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<2>, kLsuThreads, 0) == cudaSuccess && n > 0) g_lsu_ctas_per_sm[1] = n;
     }
     return e;
 }
@@ -978,12 +976,12 @@ cudaError_t launch_rows(const Member* d_members, const Tile* d_tiles, uint32_t n
 }
 
 cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool strided) {
     if (ntiles == 0) return cudaSuccess;
-    uint32_t grid = (uint32_t)sm_count * (uint32_t)g_lsu_ctas_per_sm;
+    uint32_t grid = (uint32_t)sm_count * (uint32_t)g_lsu_ctas_per_sm[strided ? 1 : 0];
     if (grid > ntiles) grid = ntiles;
-    if (g_lsu_occ == 3) tsnap_lsu_copy_kernel<3><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
-    else tsnap_lsu_copy_kernel<2><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
+    if (strided) tsnap_lsu_copy_kernel<2><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
+    else tsnap_lsu_copy_kernel<3><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
     return cudaGetLastError();
 }
 
