@@ -24,5 +24,4 @@ def test_multi_gpu_functional_check_under_torchrun():
     with open(os.path.join(out_dir, f"mgpu_check_n{n}.log"), "w") as f:
         f.write(res.stdout + "\n--- stderr ---\n" + res.stderr[-20000:])
     assert res.returncode == 0, res.stderr[-3000:]
-    ok = [ln for ln in res.stdout.splitlines() if "multi-GPU check OK" in ln]
-    assert len(ok) == n, res.stdout[-2000:]
+    assert res.stdout.count("multi-GPU check OK") == n, res.stdout[-2000:]  # (ranks' lines may interleave)
