@@ -179,6 +179,46 @@ def device_job(stats_list):
     return max(jobs, key=lambda j: (j.get("n_kernel_launches", 0), j.get("direct_bytes", 0), j.get("payload_bytes", 0)))
 
 
+class CpuMeter:
+    """Host cores actually used by this process while a timed call runs: (user + system CPU time) / wall, and the
+    largest thread count seen — measured, per rank."""
+
+    def __init__(self) -> None:
+        self.cpu_s = 0.0
+        self.wall_s = 0.0
+        self.max_threads = 0
+        self._stop = None
+
+    def start(self) -> None:
+        import psutil
+
+        self._t0 = time.perf_counter()
+        t = os.times()
+        self._c0 = t.user + t.system
+        proc = psutil.Process()
+        self._stop = threading.Event()
+
+        def watch():
+            while not self._stop.wait(0.02):
+                try:
+                    self.max_threads = max(self.max_threads, proc.num_threads())
+                except Exception:
+                    return
+
+        self._th = threading.Thread(target=watch, daemon=True)
+        self._th.start()
+
+    def stop(self) -> None:
+        t = os.times()
+        self.cpu_s += t.user + t.system - self._c0
+        self.wall_s += time.perf_counter() - self._t0
+        self._stop.set()
+        self._th.join()
+
+    def report(self) -> dict:
+        return {"cores_busy_avg": round(self.cpu_s / self.wall_s, 2) if self.wall_s else None, "threads_max": self.max_threads}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -314,8 +354,11 @@ def run_c3(ctx: Ctx, T, impl_desc: str) -> None:
     if rank == 0:
         sampler.start()
     step_ms, per_step = [], []
+    cpu = CpuMeter()
     for k in range(a.steps):
+        cpu.start()
         ms, _ = ctx.timed(lambda: T.Snapshot.take(ctx.path(f"step{k}"), app_state))
+        cpu.stop()
         step_ms.append(ms)
         if ours:
             per_step.append(device_job(S.LAST_STATS.get("save")))
@@ -384,6 +427,9 @@ def run_c3(ctx: Ctx, T, impl_desc: str) -> None:
     line["restore"] = {"value": payload_total / 1e9 / (mean(restore_ms) / 1e3), "unit": "GB/s", "ms": mean(restore_ms), "verified_all_tensors_all_ranks": ok,
                        "scatter_kernel_ms": load_stats.get("kernel_ms")}
     line["clocks"] = clocks
+    host_cpu = cpu.report()
+    line["host_cpu_during_take"] = {"cores_busy_avg_max_over_ranks": ctx.max(host_cpu["cores_busy_avg"] or 0.0), "threads_max_rank0": host_cpu["threads_max"],
+                                    "definition": "(user+system CPU seconds of the rank's process) / wall seconds over the timed takes; threads = peak thread count of the process"}
     line["payload_bytes_per_rank"] = int(payload_local)
     line["gpu_launches"] = int(launches)
 
@@ -450,8 +496,9 @@ def run_c3(ctx: Ctx, T, impl_desc: str) -> None:
         if rank == 0 and world == 1 and not a.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_c3(ctx, local)
     else:
-        line["cpu_baseline"] = {"value": take_gbs, "unit": "GB/s", "kind": "reference", "cores": reference_threads(),
-                                "host_cores_available": os.cpu_count(),
+        line["cpu_baseline"] = {"value": take_gbs, "unit": "GB/s", "kind": "reference", "cores": round(line["host_cpu_during_take"]["cores_busy_avg_max_over_ranks"], 2),
+                                "cores_definition": "measured: CPU seconds / wall seconds of one rank's process during the timed takes (max over ranks); the pipeline's thread budget is 1 + 4 + 16 per rank (T:scheduler.py:32, T:knobs.py:38)",
+                                "threads_max_rank0": host_cpu["threads_max"], "host_cores_available": os.cpu_count(),
                                 "sample": "the whole workload on every rank (no sampling): same app_state, same ranks, same target directory as the other arm"}
     if rank == 0:
         emit(line)
