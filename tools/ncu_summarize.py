@@ -32,7 +32,8 @@ for i, r in enumerate(data):
         v = g(r, k); u = unit(k)
         return v / {"byte": 1e9, "Kbyte": 1e6, "Mbyte": 1e3, "Gbyte": 1.0}.get(u, 1e9)
     rd, wr = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
-    case = labels[i // 2] if labels and i // 2 < len(labels) else ""
+    per = max(1, len(data) // len(labels)) if labels else 1
+    case = labels[i // per] if labels and i // per < len(labels) else ""
     lines.append(f"| {i} | `{name}` | {case} | {int(g(r, 'launch__grid_size'))} x {int(g(r, 'launch__block_size'))} | {int(g(r, 'launch__registers_per_thread'))} | {us:.1f} | {rd:.3f} + {wr:.3f} | {(rd + wr) / (us / 1e6):.0f} | {g(r, 'l1tex__t_sector_hit_rate.pct'):.1f} | {g(r, 'lts__t_sector_hit_rate.pct'):.1f} |")
 with open(out + "_table.md", "w") as f:
     f.write("\n".join(lines) + "\n")
