@@ -1,6 +1,7 @@
 # GPU run 6 (1 GPU): final N=1 artefacts — bench both arms, trace diagnosis, kernel cases, launch list, ncu full capture
 # (exported to CSV on the box; the .ncu-rep is dropped if it would blow the 64 MiB return limit)
 mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 400 -p no:cacheprovider > gpurun_out/r02_t6_full.log 2>&1; tail -4 gpurun_out/r02_t6_full.log
 timeout 300 python tools/sweep_sink.py --set trace > gpurun_out/r02_trace_diag.jsonl 2> gpurun_out/r02_trace_diag.err
 timeout 300 python tools/kernel_cases.py > gpurun_out/r02_kernel_cases_final.jsonl 2> gpurun_out/r02_kernel_cases_final.err
 timeout 500 python bench.py --steps 10 --warmup 3 --trace-dir gpurun_out/r02_trace > gpurun_out/r02_bench_n1_d.json 2> gpurun_out/r02_bench_n1_d.err; cut -c1-200 gpurun_out/r02_bench_n1_d.json

@@ -762,7 +762,7 @@ static int build_waves(tsnap_job* job) {
     }
     const bool single = staged_total <= A;
     const uint64_t cap = single ? A : (A / 2) / 256 * 256;
-    std::vector<int> direct_files;
+    std::vector<int> direct_files, staged_files;
     for (size_t i = 0; i < job->files.size(); ++i) {
         FileSpec& f = job->files[i];
         if (f.host_only || f.nbytes == 0) continue;
@@ -773,15 +773,52 @@ static int build_waves(tsnap_job* job) {
             job->stats.direct_bytes += f.nbytes;
             continue;
         }
+        staged_files.push_back(int(i));
+    }
+    // A job that fits the arena is still cut in two launches so that the link never waits for a full-size kernel:
+    // on save a small head wave (its D2H starts ~0.1 ms after submit while the big pack launch runs behind it), on
+    // restore a small tail wave (the only scatter that nothing overlaps is ~0.1 ms instead of the whole payload's 5 ms).
+    size_t split = SIZE_MAX;  // first file of the second wave
+    if (single && staged_total > (1ull << 30) && staged_files.size() >= 2) {
+        const uint64_t small = 128ull << 20;
+        uint64_t acc = 0;
+        if (job->kind == kSave) {
+            for (size_t k = 0; k + 1 < staged_files.size(); ++k) {
+                acc += align_up(job->files[staged_files[k]].nbytes, 256);
+                if (acc >= small) {
+                    split = k + 1;
+                    break;
+                }
+            }
+        } else if (job->kind == kLoad) {
+            for (size_t k = staged_files.size() - 1; k >= 1; --k) {
+                acc += align_up(job->files[staged_files[k]].nbytes, 256);
+                if (acc >= small) {
+                    split = k;
+                    break;
+                }
+            }
+        }
+    }
+    for (size_t k = 0; k < staged_files.size(); ++k) {
+        FileSpec& f = job->files[staged_files[k]];
         const uint64_t fb = align_up(f.nbytes, 256);
-        if (job->waves.empty() || job->waves.back().bytes + fb > cap) job->waves.emplace_back();
+        if (job->waves.empty() || job->waves.back().bytes + fb > cap || k == split) job->waves.emplace_back();
         Wave& w = job->waves.back();
         f.arena_off = w.bytes;
         f.wave = int(job->waves.size()) - 1;
         w.bytes += fb;
-        w.files.push_back(int(i));
+        w.files.push_back(staged_files[k]);
     }
-    for (size_t i = 0; i < job->waves.size(); ++i) job->waves[i].region_off = single ? 0 : (i % 2) * cap;
+    if (single) {
+        uint64_t off = 0;  // waves of a job that fits sit side by side
+        for (Wave& w : job->waves) {
+            w.region_off = off;
+            off += w.bytes;
+        }
+    } else {
+        for (size_t i = 0; i < job->waves.size(); ++i) job->waves[i].region_off = (i % 2) * cap;
+    }
     job->n_staged_waves = job->waves.size();
     job->stats.n_waves = job->waves.size();
     job->stats.arena_bytes = job->waves.empty() ? 0 : A;
