@@ -643,11 +643,11 @@ __device__ __forceinline__ void vec_put(uint32_t (&w)[4], int i, T x) {
 // kModeTranspose: dim A is unit-stride on the source, dim B on the destination.  One tile = side x side elements of
 // (A, B) for one index of the remaining dims: read with consecutive threads along A, write with consecutive threads
 // along B, through a padded shared-memory tile — both sides see full-line accesses instead of an element gather.
-template <typename T, int kSide>
+template <typename T, int kA, int kB>
 __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index, unsigned char* tbuf) {
     const uint32_t A = m.shift & 255, B = (m.shift >> 8) & 255;
     const uint64_t sA = (uint64_t)m.osize[A], sB = (uint64_t)m.osize[B];
-    const uint32_t tilesA = (uint32_t)((sA + kSide - 1) / kSide), tilesB = (uint32_t)((sB + kSide - 1) / kSide);
+    const uint32_t tilesA = (uint32_t)((sA + kA - 1) / kA), tilesB = (uint32_t)((sB + kB - 1) / kB);
     const uint32_t ib = index % tilesB;
     uint32_t rest = index / tilesB;
     const uint32_t ia = rest % tilesA;
@@ -661,17 +661,19 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
         so += (int64_t)idx * m.sstride[i];
         dofs += (int64_t)idx * m.dstride[i];
     }
-    const uint64_t a0 = (uint64_t)ia * kSide, b0 = (uint64_t)ib * kSide;
-    const uint32_t na = (uint32_t)(sA - a0 < (uint64_t)kSide ? sA - a0 : kSide);
-    const uint32_t nb = (uint32_t)(sB - b0 < (uint64_t)kSide ? sB - b0 : kSide);
+    const uint64_t a0 = (uint64_t)ia * kA, b0 = (uint64_t)ib * kB;
+    const uint32_t na = (uint32_t)(sA - a0 < (uint64_t)kA ? sA - a0 : kA);
+    const uint32_t nb = (uint32_t)(sB - b0 < (uint64_t)kB ? sB - b0 : kB);
     const int64_t ssB = m.sstride[B], dsA = m.dstride[A];
     const char* sp = reinterpret_cast<const char*>(m.src) + so + (int64_t)a0 * m.sstride[A] + (int64_t)b0 * ssB;
     char* dp = reinterpret_cast<char*>(m.dst) + dofs + (int64_t)a0 * dsA + (int64_t)b0 * m.dstride[B];
-    T(*tile)[kSide + 1] = reinterpret_cast<T(*)[kSide + 1]>(tbuf);
-    constexpr int V = 16 / (int)sizeof(T);             // elements per 16 B vector
-    constexpr int kVecPerRow = kSide / V;
-    constexpr int kIter = kSide * kVecPerRow / kLsuThreads;
-    const bool full = na == (uint32_t)kSide && nb == (uint32_t)kSide && ((reinterpret_cast<uint64_t>(sp) | (uint64_t)ssB) & 15) == 0 &&
+    T(*tile)[kA + 1] = reinterpret_cast<T(*)[kA + 1]>(tbuf);  // tile[b][a], one element of padding per row
+    constexpr int V = 16 / (int)sizeof(T);  // elements per 16 B vector
+    constexpr int kVecIn = kA / V;          // vectors per source row (along A)
+    constexpr int kVecOut = kB / V;         // vectors per destination row (along B)
+    constexpr int kIter = kB * kVecIn / kLsuThreads;
+    static_assert(kB * kVecIn == kA * kVecOut && kIter * kLsuThreads == kB * kVecIn, "tile geometry");
+    const bool full = na == (uint32_t)kA && nb == (uint32_t)kB && ((reinterpret_cast<uint64_t>(sp) | (uint64_t)ssB) & 15) == 0 &&
                       ((reinterpret_cast<uint64_t>(dp) | (uint64_t)dsA) & 15) == 0;
     if (full) {
         // interior tile: 16 B vectors on both global sides, all loads in flight before the first shared-memory store
@@ -679,12 +681,12 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
 #pragma unroll
         for (int k = 0; k < kIter; ++k) {
             const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
-            r[k] = ld_stream16(sp + (int64_t)(idx / kVecPerRow) * ssB + (idx % kVecPerRow) * 16);
+            r[k] = ld_stream16(sp + (int64_t)(idx / kVecIn) * ssB + (idx % kVecIn) * 16);
         }
 #pragma unroll
         for (int k = 0; k < kIter; ++k) {
             const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
-            const uint32_t b = idx / kVecPerRow, v = idx % kVecPerRow;
+            const uint32_t b = idx / kVecIn, v = idx % kVecIn;
 #pragma unroll
             for (int i = 0; i < V; ++i) tile[b][v * V + i] = vec_get<T>(r[k], i);
         }
@@ -692,7 +694,7 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
 #pragma unroll
         for (int k = 0; k < kIter; ++k) {
             const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
-            const uint32_t a = idx / kVecPerRow, v = idx % kVecPerRow;
+            const uint32_t a = idx / kVecOut, v = idx % kVecOut;
             uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int i = 0; i < V; ++i) vec_put<T>(w, i, tile[v * V + i][a]);
@@ -701,21 +703,23 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
         return;  // the caller's loop synchronises before the tile buffer is reused
     }
     // edge tiles / unaligned bases: element accesses, still coalesced on both sides
-    constexpr int kRowsPerPass = kLsuThreads / kSide;
-    const uint32_t tx = threadIdx.x % kSide, ty = threadIdx.x / kSide;
-    for (uint32_t b = ty; b < nb; b += kRowsPerPass)
-        if (tx < na) tile[b][tx] = __ldg(reinterpret_cast<const T*>(sp + (int64_t)b * ssB) + tx);
+    for (uint32_t e = threadIdx.x; e < nb * (uint32_t)kA; e += kLsuThreads) {
+        const uint32_t b = e / kA, a = e % kA;
+        if (a < na) tile[b][a] = __ldg(reinterpret_cast<const T*>(sp + (int64_t)b * ssB) + a);
+    }
     __syncthreads();
-    for (uint32_t a = ty; a < na; a += kRowsPerPass)
-        if (tx < nb) reinterpret_cast<T*>(dp + (int64_t)a * dsA)[tx] = tile[tx][a];
+    for (uint32_t e = threadIdx.x; e < na * (uint32_t)kB; e += kLsuThreads) {
+        const uint32_t a = e / kB, b = e % kB;
+        if (b < nb) reinterpret_cast<T*>(dp + (int64_t)a * dsA)[b] = tile[b][a];
+    }
 }
 
 __device__ __noinline__ void tile_transpose(const Member& m, uint32_t index, unsigned char* tbuf) {
-    switch (m.unit) {
-        case 8: tile_transpose_t<uint64_t, 64>(m, index, tbuf); break;
-        case 4: tile_transpose_t<uint32_t, 64>(m, index, tbuf); break;
-        case 2: tile_transpose_t<uint16_t, 128>(m, index, tbuf); break;
-        default: tile_transpose_t<uint8_t, 128>(m, index, tbuf); break;
+    switch (m.unit) {  // geometry = plan.h transpose_side_a / transpose_side_b
+        case 8: tile_transpose_t<uint64_t, 64, 64>(m, index, tbuf); break;
+        case 4: tile_transpose_t<uint32_t, 128, 64>(m, index, tbuf); break;
+        case 2: tile_transpose_t<uint16_t, 128, 128>(m, index, tbuf); break;
+        default: tile_transpose_t<uint8_t, 128, 128>(m, index, tbuf); break;
     }
 }
 
@@ -871,8 +875,10 @@ __global__ void __launch_bounds__(kLsuThreads, kMinBlocks) tsnap_lsu_copy_kernel
     __shared__ Member sm;
     __shared__ __align__(16) unsigned char tbuf[64 * 65 * 8];  // transpose tile: 64 x 65 x 8 B >= 128 x 129 x 2 B
     uint32_t loaded = 0xffffffffu;
+    Tile next = blockIdx.x < ntiles ? tiles[blockIdx.x] : Tile{0, 0};
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const Tile tl = tiles[t];
+        const Tile tl = next;
+        if (t + gridDim.x < ntiles) next = tiles[t + gridDim.x];  // the descriptor of the next tile is in flight behind this tile's work
         // stage the member record in shared memory: every thread needs all of it (consecutive tiles of a CTA mostly
         // belong to the same member: reload only on change)
         __syncthreads();  // also fences the previous tile's use of sm / tbuf

@@ -39,9 +39,10 @@ struct Dim {
 };
 
 static bool tile_fits_u32(const Member& m, int a, int b, uint32_t esz) {
-    const uint32_t side = transpose_side(esz);
+    const uint32_t sa = transpose_side_a(esz), sb = transpose_side_b(esz);
     long double n = 1;
-    for (uint32_t i = 0; i < m.nouter; ++i) n *= (int(i) == a || int(i) == b) ? (long double)((uint64_t(m.osize[i]) + side - 1) / side) : (long double)m.osize[i];
+    for (uint32_t i = 0; i < m.nouter; ++i)
+        n *= int(i) == a ? (long double)((uint64_t(m.osize[i]) + sa - 1) / sa) : int(i) == b ? (long double)((uint64_t(m.osize[i]) + sb - 1) / sb) : (long double)m.osize[i];
     return n < 4.0e9L;
 }
 

@@ -65,16 +65,19 @@ struct Tile {
 inline bool engine_mode(uint32_t mode) { return mode == kModeBulk || mode == kModeRows; }  // copy-engine kernels
 inline uint32_t tile_bytes_for(uint32_t mode) { return engine_mode(mode) ? kTileBulk : kTileLsu; }
 
-// kModeTranspose: elements per tile side (a tile is side x side elements of the two unit-stride dims)
-inline uint32_t transpose_side(uint32_t esz) { return esz >= 4 ? 64 : 128; }
+// kModeTranspose: elements per tile along A (the source-contiguous dim) and B (the destination-contiguous dim);
+// 32 KiB of payload per tile except for 1-byte elements (16 KiB)
+inline uint32_t transpose_side_a(uint32_t esz) { return esz == 8 ? 64 : 128; }
+inline uint32_t transpose_side_b(uint32_t esz) { return esz >= 4 ? 64 : 128; }
 
 // number of tiles a member needs
 inline uint64_t tile_count(const Member& m) {
     if (m.bytes == 0) return 0;
     if (m.mode == kModeTranspose) {
-        const uint32_t a = m.shift & 255, b = (m.shift >> 8) & 255, side = transpose_side(m.unit);
+        const uint32_t a = m.shift & 255, b = (m.shift >> 8) & 255, sa = transpose_side_a(m.unit), sb = transpose_side_b(m.unit);
         uint64_t n = 1;
-        for (uint32_t i = 0; i < m.nouter; ++i) n *= (i == a || i == b) ? (uint64_t(m.osize[i]) + side - 1) / side : uint64_t(m.osize[i]);
+        for (uint32_t i = 0; i < m.nouter; ++i)
+            n *= i == a ? (uint64_t(m.osize[i]) + sa - 1) / sa : i == b ? (uint64_t(m.osize[i]) + sb - 1) / sb : uint64_t(m.osize[i]);
         return n;
     }
     if (engine_mode(m.mode)) return (m.bytes + kTileBulk - 1) / kTileBulk;
