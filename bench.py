@@ -792,7 +792,55 @@ def run_c5(ctx: Ctx, T, impl_desc: str) -> None:
         emit(line)
 
 
-RUNNERS = {"c2": run_c2, "c3": run_c3, "c4": run_c4, "c5": run_c5}
+# ---- C1: single-process 1 GiB fp32 nn.Linear on the CPU (the reference's own CPU-runnable case, no GPU involved) ----
+def run_c1(ctx: Ctx, T, impl_desc: str) -> None:
+    a = ctx.args
+    torch.manual_seed(0)
+    n = 1024 if a.cpu_dryrun else 16384
+    model = torch.nn.Linear(n, n)
+    app = {"model": model}
+    payload = sum(t.numel() * t.element_size() for t in model.state_dict().values())
+    for w in range(a.warmup):
+        T.Snapshot.take(ctx.path(f"warm{w}"), app)
+        ctx.cleanup(f"warm{w}")
+    take_ms, cpu = [], CpuMeter()
+    for k in range(a.steps):
+        cpu.start()
+        t0 = time.perf_counter()
+        T.Snapshot.take(ctx.path(f"step{k}"), app)
+        take_ms.append((time.perf_counter() - t0) * 1e3)
+        cpu.stop()
+        if k + 1 < a.steps:
+            ctx.cleanup(f"step{k}")
+    keep = f"step{a.steps - 1}"
+    want = {k: v.clone() for k, v in model.state_dict().items()}
+    restore_ms = []
+    for _ in range(min(a.steps, 3)):
+        with torch.no_grad():
+            for v in model.state_dict().values():
+                v.zero_()
+        t0 = time.perf_counter()
+        T.Snapshot(ctx.path(keep)).restore(app)
+        restore_ms.append((time.perf_counter() - t0) * 1e3)
+    ok = all(torch.equal(want[k], v) for k, v in model.state_dict().items())
+    ctx.cleanup(keep)
+    ms = mean(take_ms)
+    config = {"workload": f"C1: single-process Snapshot.take of a 1 GiB fp32 nn.Linear({n},{n}) state_dict held on the CPU to local fs (no GPU on the path)",
+              "world_size": 1, "payload_bytes_total": int(payload), "target_fs": a.target_fs, "_dtype": "fp32 (byte copy)", "semantics": "returned (no fsync)",
+              "l2": "n/a (host path)"}
+    line = common_line(ctx, impl_desc, "checkpoint_save_GBps", payload / 1e9 / (ms / 1e3), "GB/s", ms, config)
+    line["n_gpus"] = 0
+    line["e2e"] = {"value": line["value"], "unit": "GB/s", "ms_per_step": ms, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "definition": "Snapshot.take wall clock; host tensors, host engine"}
+    line["steps_ms"] = [round(x, 1) for x in take_ms]
+    line["restore"] = {"value": payload / 1e9 / (mean(restore_ms) / 1e3), "unit": "GB/s", "ms": mean(restore_ms), "verified": ok}
+    line["host_cpu_during_take"] = cpu.report()
+    line["gpu_launches"] = 0
+    if a.impl == "reference":
+        line["cpu_baseline"] = {"value": line["value"], "unit": "GB/s", "kind": "reference", "cores": cpu.report()["cores_busy_avg"], "host_cores_available": os.cpu_count(), "sample": "whole workload"}
+    emit(line)
+
+
+RUNNERS = {"c1": run_c1, "c2": run_c2, "c3": run_c3, "c4": run_c4, "c5": run_c5}
 
 
 def fs_kind(path: str) -> str:
@@ -840,7 +888,7 @@ def main() -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.cpu_dryrun:
+    if args.cpu_dryrun or args.config == "c1":
         device = torch.device("cpu")
     elif not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback for device tensors")

@@ -43,7 +43,7 @@ def test_c3_reference_arm_is_the_unmodified_reference_on_the_same_config():
     assert ref["restore"]["verified_all_tensors_all_ranks"] is True
 
 
-@pytest.mark.parametrize("cfg", ["c2", "c5"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c5"])
 def test_other_configs_run(cfg):
     d = _run("--config", cfg)
     assert d["value"] > 0 and d["config"]["workload"].startswith(cfg.upper())

@@ -35,6 +35,14 @@ d = load("c3_n1_ours.json")
 if d:
     out += ["", f"N=1 detail: steps (ms) {d.get('steps_ms')}; engine of the last step {json.dumps(d.get('engine_step'))};",
             f"cpu_baseline {json.dumps(d.get('cpu_baseline'))}; timeline {json.dumps(d.get('timeline'))}."]
+c1 = [(tag, load(f"c1_{tag}_ours.json"), load(f"c1_{tag}_reference.json")) for tag in ("buildbox", "gpubox")]
+if any(a and b for _, a, b in c1):
+    out += ["", "## C1 — single-process 1 GiB fp32 nn.Linear on the CPU (no GPU on the path; the host engine: planner + native pwrite/pread workers)", "",
+            "| host | arm | take GB/s | take ms (each) | restore GB/s | cores busy |", "|---|---|---|---|---|---|"]
+    for tag, a, b in c1:
+        for arm, d in (("ours", a), ("reference", b)):
+            if d:
+                out.append(f"| {tag} ({d['host']['cpu_count']} hw threads) | {arm} | **{f(d['value'], 2)}** | {d['steps_ms']} | {f(d['restore']['value'], 2)} | {d['host_cpu_during_take']['cores_busy_avg']} |")
 out += ["", "## C2 — DDP ResNet-50 + Adam, replicated=['**'] (0.31 GB, ≈800 tensors, 0-d scalars, CPU `step` slab chain)", "",
         "| N | arm | take ms | take GB/s | restore ms | control plane / engine job (ms) | collectives per take | LSU + bulk kernel ms |", "|---|---|---|---|---|---|---|---|"]
 for n in (2, 8):
