@@ -444,10 +444,11 @@ def run_c3(ctx: Ctx, T, impl_desc: str) -> None:
             "pack_kernel_ms": kernel_ms,
             "d2h_span_ms": copy_ms,
             "gbs": payload_total / 1e9 / ((kernel_ms + copy_ms) / 1e3) if kernel_ms + copy_ms > 0 else None,
-            "definition": "device side of the same timed takes: CUDA-event time of the pack kernels + first-to-last D2H span on the copy stream (includes waits for free pinned slots, i.e. back-pressure from the writers); max over ranks",
+            "link_starved_ms": ctx.max(mean(st.get("link_starved_ms", 0.0) for st in per_step)),
+            "definition": "device side of the same timed takes: CUDA-event time of the pack kernels + first-to-last D2H span on the copy stream (includes waits for free pinned slots, i.e. back-pressure from the writers); link_starved_ms = time the link idled for want of a pinned slot (no copy queued); max over ranks",
         }
         line["engine_step"] = {k: last.get(k) for k in ("plan_ms", "kernel_ms", "copy_ms", "device_done_ms", "total_ms", "n_files", "n_members", "n_tiles_bulk", "n_tiles_lsu",
-                                                           "n_kernel_launches", "arena_bytes", "n_waves", "direct_bytes", "n_memcpy", "slot_wait_ms", "io_busy_ms", "io_queue_ms")}
+                                                           "n_kernel_launches", "arena_bytes", "n_waves", "direct_bytes", "n_memcpy", "slot_wait_ms", "link_starved_ms", "io_busy_ms", "io_queue_ms")}
         line["take_phases_ms"] = {k: round(v, 2) for k, v in take_phases.items()}
         line["write_phases_ms"] = {k: round(v, 2) for k, v in write_phases.items()}
         line["host"]["engine_io_threads_per_rank"] = eng.io_threads

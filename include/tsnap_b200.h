@@ -197,6 +197,9 @@ typedef struct tsnap_job_stats {
     uint64_t bytes_rows;        /* logical bytes moved run by run by the rows (TMA) kernel   */
     uint64_t n_tiles_rows;
     double kernel_rows_ms;
+    double link_starved_ms;     /* part of slot_wait_ms during which NO payload copy was queued or running on the copy
+                                   stream: the link really idled for want of a pinned slot (slot_wait_ms alone also
+                                   counts waits behind a full queue of copies, which cost nothing)            */
 } tsnap_job_stats;
 int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out);
 

@@ -124,6 +124,7 @@ class JobStats(C.Structure):
         ("bytes_rows", C.c_uint64),
         ("n_tiles_rows", C.c_uint64),
         ("kernel_rows_ms", C.c_double),
+        ("link_starved_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:

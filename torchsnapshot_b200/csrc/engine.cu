@@ -578,7 +578,7 @@ static int plan_wave(tsnap_job* job, Wave& w) {
                 if (nt == 0) continue;
                 const uint32_t mi = uint32_t(w.members.size());
                 w.members.push_back(m);
-                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : m.mode == kModeStrided ? w.tiles_strided : w.tiles_lsu;
+                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : m.mode == kModeStrided ? w.tiles_strided : m.mode == kModeTranspose ? w.tiles_transpose : w.tiles_lsu;
                 (m.mode == kModeBulk ? job->stats.bytes_bulk : m.mode == kModeRows ? job->stats.bytes_rows : job->stats.bytes_lsu) += m.bytes;
                 for (uint64_t t = 0; t < nt; ++t) tv.push_back(Tile{mi, uint32_t(t)});
             }
@@ -586,7 +586,7 @@ static int plan_wave(tsnap_job* job, Wave& w) {
     }
     job->stats.n_tiles_bulk += w.tiles_bulk.size();
     job->stats.n_tiles_rows += w.tiles_rows.size();
-    job->stats.n_tiles_lsu += w.tiles_lsu.size() + w.tiles_strided.size();
+    job->stats.n_tiles_lsu += w.tiles_lsu.size() + w.tiles_strided.size() + w.tiles_transpose.size();
     return TSNAP_OK;
 }
 
@@ -598,7 +598,8 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     const size_t rb = w.tiles_rows.size() * sizeof(Tile);
     const size_t lb = w.tiles_lsu.size() * sizeof(Tile);
     const size_t sb2 = w.tiles_strided.size() * sizeof(Tile);
-    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256);
+    const size_t tb2 = w.tiles_transpose.size() * sizeof(Tile);
+    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256) + align_up(tb2, 256);
     CUDA_TRY(cudaEventCreate(&w.ev_k0));
     CUDA_TRY(cudaEventCreate(&w.ev_k1));
     CUDA_TRY(cudaEventCreate(&w.ev_kr));
@@ -620,23 +621,26 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     Tile* d_rows = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256));
     Tile* d_lsu = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256));
     Tile* d_strided = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256));
+    Tile* d_transpose = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256));
     // pageable sources: the runtime stages them before returning, so the vectors may be freed later
     CUDA_TRY(cudaMemcpyAsync(d_members, w.members.data(), mb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (bb) CUDA_TRY(cudaMemcpyAsync(d_bulk, w.tiles_bulk.data(), bb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (rb) CUDA_TRY(cudaMemcpyAsync(d_rows, w.tiles_rows.data(), rb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (lb) CUDA_TRY(cudaMemcpyAsync(d_lsu, w.tiles_lsu.data(), lb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (sb2) CUDA_TRY(cudaMemcpyAsync(d_strided, w.tiles_strided.data(), sb2, cudaMemcpyHostToDevice, eng->s_kernel));
-    job->stats.table_h2d_bytes += mb + bb + rb + lb + sb2;
+    if (tb2) CUDA_TRY(cudaMemcpyAsync(d_transpose, w.tiles_transpose.data(), tb2, cudaMemcpyHostToDevice, eng->s_kernel));
+    job->stats.table_h2d_bytes += mb + bb + rb + lb + sb2 + tb2;
     CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
     CUDA_TRY(launch_bulk(d_members, d_bulk, uint32_t(w.tiles_bulk.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
     CUDA_TRY(launch_rows(d_members, d_rows, uint32_t(w.tiles_rows.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_kr, eng->s_kernel));
-    CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel, false));
-    CUDA_TRY(launch_lsu(d_members, d_strided, uint32_t(w.tiles_strided.size()), eng->sm_count, eng->s_kernel, true));
+    CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel, kLsuDefault));
+    CUDA_TRY(launch_lsu(d_members, d_strided, uint32_t(w.tiles_strided.size()), eng->sm_count, eng->s_kernel, kLsuStrided));
+    CUDA_TRY(launch_lsu(d_members, d_transpose, uint32_t(w.tiles_transpose.size()), eng->sm_count, eng->s_kernel, kLsuTranspose));
     CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
-    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1) + (w.tiles_strided.empty() ? 0 : 1);
+    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1) + (w.tiles_strided.empty() ? 0 : 1) + (w.tiles_transpose.empty() ? 0 : 1);
     job->stats.n_kernel_launches += nl;
     eng->kernels_launched += nl;
     return TSNAP_OK;
@@ -1168,9 +1172,12 @@ static int run_save_inner(tsnap_job* job) {
             const uint64_t n = std::min(sb, f.nbytes - lo);
             auto tw = clk::now();
             const double tw_ms = eng->trace ? job->now_ms() : 0;
+            const bool link_idle = job->copies_in_flight.load(std::memory_order_acquire) == 0;
             char* slot = eng->ring.acquire();
             const double waited = ms_since(tw);
             job->slot_wait_us += int64_t(waited * 1000.0);
+            if (link_idle) job->link_starved_us += int64_t(waited * 1000.0);
+            job->copies_in_flight.fetch_add(1, std::memory_order_acq_rel);
             if (eng->trace && waited > 0.05) job->add_trace(TSNAP_TR_SLOT_WAIT, 0, cr.fi, tw_ms, job->now_ms(), 0);
             cudaEvent_t ev = eng->get_event();
             const double t_issue = eng->trace ? job->now_ms() : 0;
@@ -1189,6 +1196,7 @@ static int run_save_inner(tsnap_job* job) {
             const int fidx = cr.fi;
             push_pending(eng, ev, [eng, job, fp, fidx, slot, lo, n, ev, t_issue](bool evok) {
                 eng->put_event(ev);
+                job->copies_in_flight.fetch_sub(1, std::memory_order_acq_rel);
                 if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
                 if (eng->trace) {
                     // the copy engine runs the chunks of s_copy back to back: busy since the later of "issued" and
@@ -1929,6 +1937,7 @@ int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out) {
     job->stats.io_busy_ms = job->io_busy_us.load() / 1000.0;
     job->stats.io_queue_ms = job->io_queue_us.load() / 1000.0;
     job->stats.n_memcpy = uint64_t(job->n_memcpy.load());
+    job->stats.link_starved_ms = job->link_starved_us.load() / 1000.0;
     *out = job->stats;
     return TSNAP_OK;
 }

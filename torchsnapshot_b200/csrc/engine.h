@@ -171,7 +171,7 @@ struct Wave {
     uint64_t bytes = 0;       // arena bytes (256B-aligned file regions)
     uint64_t region_off = 0;  // offset of the region inside the arena
     std::vector<Member> members;
-    std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu, tiles_strided;  // strided tiles run the 2-CTA/SM build of the LSU kernel
+    std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu, tiles_strided, tiles_transpose;  // the last two run their own builds of the LSU kernel
     void* d_tables = nullptr;
     size_t table_bytes = 0, table_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_kr = nullptr, ev_k2 = nullptr;  // kernel timing: bulk | rows | lsu
@@ -223,7 +223,8 @@ struct tsnap_job {
     // stats
     tsnap_job_stats stats{};
     bool timing_collected = false;
-    std::atomic<int64_t> slot_wait_us{0}, io_busy_us{0}, io_queue_us{0}, n_memcpy{0};
+    std::atomic<int64_t> slot_wait_us{0}, io_busy_us{0}, io_queue_us{0}, n_memcpy{0}, link_starved_us{0};
+    std::atomic<int> copies_in_flight{0};  // payload chunks issued on s_copy and not yet retired
     std::chrono::steady_clock::time_point t_submit;
 
     void fail(int code, const std::string& msg);

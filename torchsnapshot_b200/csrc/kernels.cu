@@ -716,9 +716,9 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
 
 __device__ __noinline__ void tile_transpose(const Member& m, uint32_t index, unsigned char* tbuf) {
     switch (m.unit) {  // geometry = plan.h transpose_side_a / transpose_side_b
-        case 8: tile_transpose_t<uint64_t, 64, 64>(m, index, tbuf); break;
-        case 4: tile_transpose_t<uint32_t, 128, 64>(m, index, tbuf); break;
-        case 2: tile_transpose_t<uint16_t, 128, 128>(m, index, tbuf); break;
+        case 8: tile_transpose_t<uint64_t, 64, 32>(m, index, tbuf); break;
+        case 4: tile_transpose_t<uint32_t, 64, 64>(m, index, tbuf); break;
+        case 2: tile_transpose_t<uint16_t, 128, 64>(m, index, tbuf); break;
         default: tile_transpose_t<uint8_t, 128, 128>(m, index, tbuf); break;
     }
 }
@@ -867,13 +867,14 @@ __device__ __noinline__ void tile_cast(const Member& m, uint32_t index) {
 }
 
 // kMinBlocks = CTAs per SM the register allocation is bounded for: 3 caps it at 80 registers (the strided path then
-// spills), 2 at 128.  Both are built: strided tiles are launched on <2>, every other mode on <3> (kernels.h, A/B in
-// profiles/r02_kernel_cases.md).
+// spills), 2 at 128, 6 at 40.  Three builds: strided tiles run on <2>, transpose tiles on <6> (a latency-bound
+// load -> shared -> store cycle: more resident CTAs in different phases keep the memory system busy), every other mode
+// on <3> (kernels.h, A/B in profiles/r02_kernel_cases.md).
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kLsuThreads, kMinBlocks) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
                                                                             const Tile* __restrict__ tiles, uint32_t ntiles) {
     __shared__ Member sm;
-    __shared__ __align__(16) unsigned char tbuf[64 * 65 * 8];  // transpose tile: 64 x 65 x 8 B >= 128 x 129 x 2 B
+    __shared__ __align__(16) unsigned char tbuf[64 * 65 * 4 + 64];  // transpose tile: 64 x 65 x 4 B >= 64 x 129 x 2 B, 32 x 65 x 8 B, 128 x 129 B
     uint32_t loaded = 0xffffffffu;
     Tile next = blockIdx.x < ntiles ? tiles[blockIdx.x] : Tile{0, 0};
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -946,7 +947,7 @@ static void rows_launch(const Member* m, const Tile* t, uint32_t n, uint32_t gri
 
 // resident CTAs per SM of the two builds of the LSU kernel, from the occupancy calculator: each persistent grid is
 // exactly one wave
-static int g_lsu_ctas_per_sm[2] = {3, 2};
+static int g_lsu_ctas_per_sm[3] = {3, 2, 6};
 
 cudaError_t init_kernels() {
     cudaError_t e = bulk_attr<3, 16384>();
@@ -955,6 +956,7 @@ cudaError_t init_kernels() {
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<3>, kLsuThreads, 0) == cudaSuccess && n > 0) g_lsu_ctas_per_sm[0] = n;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<2>, kLsuThreads, 0) == cudaSuccess && n > 0) g_lsu_ctas_per_sm[1] = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tsnap_lsu_copy_kernel<6>, kLsuThreads, 0) == cudaSuccess && n > 0) g_lsu_ctas_per_sm[2] = n;
     }
     return e;
 }
@@ -982,11 +984,12 @@ cudaError_t launch_rows(const Member* d_members, const Tile* d_tiles, uint32_t n
 }
 
 cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
-                       cudaStream_t stream, bool strided) {
+                       cudaStream_t stream, int variant) {
     if (ntiles == 0) return cudaSuccess;
-    uint32_t grid = (uint32_t)sm_count * (uint32_t)g_lsu_ctas_per_sm[strided ? 1 : 0];
+    uint32_t grid = (uint32_t)sm_count * (uint32_t)g_lsu_ctas_per_sm[variant];
     if (grid > ntiles) grid = ntiles;
-    if (strided) tsnap_lsu_copy_kernel<2><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
+    if (variant == kLsuStrided) tsnap_lsu_copy_kernel<2><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
+    else if (variant == kLsuTranspose) tsnap_lsu_copy_kernel<6><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
     else tsnap_lsu_copy_kernel<3><<<grid, kLsuThreads, 0, stream>>>(d_members, d_tiles, ntiles);
     return cudaGetLastError();
 }

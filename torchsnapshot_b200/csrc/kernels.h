@@ -10,9 +10,12 @@ cudaError_t launch_bulk(const Member* d_members, const Tile* d_tiles, uint32_t n
                         cudaStream_t stream);
 cudaError_t launch_rows(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
                         cudaStream_t stream);
-// strided = true: the build of the LSU kernel bounded for 2 CTAs per SM (128 registers: the strided gather keeps 8
-// independent 16 B loads per thread in flight without spilling; 0.65 vs 0.47 of peak on 128 B runs).  All other modes
-// run the 3-CTA build (80 registers: 0.84 / 0.92 of peak on unaligned dense runs / casts vs 0.74 / 0.85).
+// Which build of the LSU kernel a tile list runs on (register bound = resident CTAs per SM):
+//   kLsuDefault   3 CTAs/SM, 80 registers: unaligned dense runs 0.85, casts 0.93 of the measured HBM peak (0.74 / 0.85 on the 2-CTA build)
+//   kLsuStrided   2 CTAs/SM, 128 registers: the strided gather keeps 8 independent 16 B loads per thread in flight without
+//                 spilling (0.66 vs 0.47 on 128 B runs)
+//   kLsuTranspose 6 CTAs/SM, 40 registers: 16 KiB tiles, more CTAs in different phases of the load -> shared -> store cycle
+enum LsuVariant { kLsuDefault = 0, kLsuStrided = 1, kLsuTranspose = 2 };
 cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
-                       cudaStream_t stream, bool strided);
+                       cudaStream_t stream, int variant);
 }  // namespace tsnap

@@ -65,10 +65,10 @@ struct Tile {
 inline bool engine_mode(uint32_t mode) { return mode == kModeBulk || mode == kModeRows; }  // copy-engine kernels
 inline uint32_t tile_bytes_for(uint32_t mode) { return engine_mode(mode) ? kTileBulk : kTileLsu; }
 
-// kModeTranspose: elements per tile along A (the source-contiguous dim) and B (the destination-contiguous dim);
-// 32 KiB of payload per tile except for 1-byte elements (16 KiB)
-inline uint32_t transpose_side_a(uint32_t esz) { return esz == 8 ? 64 : 128; }
-inline uint32_t transpose_side_b(uint32_t esz) { return esz >= 4 ? 64 : 128; }
+// kModeTranspose: elements per tile along A (the source-contiguous dim) and B (the destination-contiguous dim):
+// 16 KiB of payload per tile (4 x 16 B vectors per thread), small enough for 6 resident CTAs per SM
+inline uint32_t transpose_side_a(uint32_t esz) { return esz >= 4 ? 64 : 128; }
+inline uint32_t transpose_side_b(uint32_t esz) { return esz == 8 ? 32 : esz == 1 ? 128 : 64; }
 
 // number of tiles a member needs
 inline uint64_t tile_count(const Member& m) {
