@@ -71,6 +71,14 @@ class BatchedBufferStager(BufferStager):
         descs, keep = self.native_descs(0)
         if not descs:
             return memoryview(bytes(self.slab_sz_bytes))
+        if len({(t.device.type, t.device.index) for t in keep if t.is_cuda}) > 1:
+            # members on several GPUs of this process (the slab assignment keys on is_cuda only, T:batcher.py:300-303):
+            # every member is staged by the engine of its own device, the slab is assembled on the host
+            slab = bytearray(self.slab_sz_bytes)
+            for (lo, hi), stager in self.byte_range_to_buffer_stager.items():
+                if hi > lo:
+                    slab[lo:hi] = await stager.stage_buffer(executor)
+            return memoryview(slab)
         staged = engine_for(keep[0]).stage(descs, self.slab_sz_bytes, stream=current_stream_of(keep[0]), keepalive=keep)
         if executor is not None:
             return await asyncio.get_running_loop().run_in_executor(executor, staged.wait)

@@ -72,6 +72,14 @@ def _engine_key(tensors: List[torch.Tensor]) -> int:
     return -1
 
 
+def _one_device(tensors: List[torch.Tensor]) -> bool:
+    """A request goes to ONE engine (one GPU).  A slab whose members live on several GPUs of this process (the batcher
+    keys GPU slabs by is_cuda only, like T:batcher.py:300-303) is left to its own stage_buffer, which stages member by
+    member through each tensor's engine."""
+    devs = {t.device.index if t.device.index is not None else torch.cuda.current_device() for t in tensors if t.is_cuda}
+    return len(devs) <= 1
+
+
 class _NativeJobs:
     """One engine job per device that appears in the plan."""
 
@@ -174,6 +182,8 @@ async def execute_write_reqs(
     total = 0
     for wr in write_reqs:
         described = describe_stager(wr.buffer_stager) if root is not None else None
+        if described is not None and not _one_device(described[1]):
+            described = None
         if described is not None:
             descs, keep, nbytes = described
             if native is None:
@@ -379,6 +389,8 @@ async def execute_read_reqs(
     described_reqs = []
     for rr in read_reqs:
         described = describe_consumer(rr.buffer_consumer) if root is not None else None
+        if described is not None and not _one_device(described[1]):
+            described = None
         if described is not None:
             descs, keep, wire_nbytes = described
             if rr.byte_range is not None:
