@@ -1,5 +1,6 @@
 # GPU run 8 (1 GPU): tests after the transpose-build change, kernel cases, C1 on the GPU box's host, short bench (link_starved_ms)
 mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -1 gpurun_out/r02_smoke.log
 timeout 1200 python -m pytest tests -m gpu -q --timeout 400 -p no:cacheprovider > gpurun_out/r02_t8_full.log 2>&1; tail -4 gpurun_out/r02_t8_full.log
 timeout 300 python tools/kernel_cases.py > gpurun_out/r02_kernel_cases_final.jsonl 2> gpurun_out/r02_kernel_cases_final.err
 python -c "
