@@ -7,6 +7,8 @@ broadcasts the result.  Only ownership metadata crosses ranks; tensor bytes neve
 from __future__ import annotations
 
 import copy
+import hashlib
+import pickle
 import os
 from collections import defaultdict
 from dataclasses import dataclass
@@ -103,9 +105,21 @@ def _partition_replicated_write_reqs(
     for path, wrs in write_reqs.items():
         for i, wr in enumerate(wrs):
             loads[path].append(_WriteLoad(path, i, _write_size(wr)))
-    gathered = [None] * pg.get_world_size()
-    pg.all_gather_object(gathered, (entries, loads, non_replicated_size))
-    all_entries, all_loads, all_sizes = zip(*gathered)
+    world = pg.get_world_size()
+    # Replicated state is, by definition, the same on every rank (DDP): instead of shipping every rank's ~1000 entries to
+    # every rank (O(world x entries) pickling per take: 18 ms of a 59 ms C2 take at 8 ranks), ranks first exchange a digest
+    # of their replicated plan plus the one number that differs (their non-replicated bytes).  Only when the digests
+    # disagree (partially replicated DTensors, diverging state) is the reference's full exchange needed
+    # (T:partitioner.py:140-213).
+    digest = hashlib.sha1(pickle.dumps((list(entries.items()), {k: [(w.write_req_idx, w.size) for w in v] for k, v in loads.items()}), protocol=4)).hexdigest()
+    brief = [None] * world
+    pg.all_gather_object(brief, (digest, non_replicated_size))
+    if all(b[0] == digest for b in brief):
+        all_entries, all_loads, all_sizes = [entries] * world, [loads] * world, [b[1] for b in brief]
+    else:
+        gathered = [None] * world
+        pg.all_gather_object(gathered, (entries, loads, non_replicated_size))
+        all_entries, all_loads, all_sizes = zip(*gathered)
     # The reference lets rank 0 partition and broadcasts the result (T:partitioner.py:176-192).  The greedy
     # assignment is a pure function of the gathered inputs, so every rank evaluates it locally: one collective less.
     result = _partition_write_loads(list(all_entries), list(all_loads), list(all_sizes), pg.get_world_size())
