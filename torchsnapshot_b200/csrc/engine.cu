@@ -1103,6 +1103,9 @@ static int run_save_inner(tsnap_job* job) {
         if (cudaEventCreate(&job->ev_copy_begin) != cudaSuccess || cudaEventCreate(&job->ev_copy_end) != cudaSuccess)
             return bail(set_err(TSNAP_ECUDA, "event create failed"));
     }
+    // the "direct copies finished" notification is retired by the completion thread AFTER the wave's chunk entries, i.e.
+    // possibly after the last write: it keeps the job alive with a part of its own
+    if (has_direct) parts += 1;
     account_parts(job, parts);
     if (nw == 0) mark_device_done(job);
     if (parts == 0) return TSNAP_OK;
@@ -1226,10 +1229,11 @@ static int run_save_inner(tsnap_job* job) {
         }
         if (wi + 1 == nw) cudaEventRecord(job->ev_copy_end, eng->s_copy);
         if (cudaEventRecord(w.ev_copied, eng->s_copy) != cudaSuccess) job->fail(TSNAP_ECUDA, "event record failed");
-        if (w.direct)
+        if (w.direct)  // (this entry is queued behind the wave's chunk entries: it holds a part of its own, see below)
             push_pending(eng, w.ev_copied, [job](bool evok) {
                 if (!evok) job->fail(TSNAP_ECUDA, "D2H copy failed");
                 mark_device_done(job);
+                job->part_done();
             });
         if (launched < ns) {
             rc = launch_next();
@@ -1240,6 +1244,7 @@ static int run_save_inner(tsnap_job* job) {
                 int64_t remaining = 0;
                 for (size_t wj = wi + 1; wj < nw; ++wj)
                     for (int fj : job->waves[wj].files) remaining += job->files[fj].parts_left.load();
+                if (has_direct) remaining += 1;  // the direct wave's completion entry is never queued either
                 for (int64_t i = 0; i < remaining; ++i) job->part_done();
                 return TSNAP_OK;
             }
