@@ -80,7 +80,8 @@ open(os.path.join(ROOT, "profiles", "r02_bench_summary.md"), "w").write("\n".joi
 # ---- kernel cases -----------------------------------------------------------------------------------------------------
 kc = ["# r02 — every kernel mode in isolation (CUDA events, `tools/kernel_cases.py`, 1 GiB-class members, N=1)", "",
       "`frac` = algorithmic bytes (read + written) / kernel time / 6565.8 GB/s (MEASURED_PEAKS.json).  Variants: LSU kernel bounded for 2 (128 regs) or 3 (80 regs) CTAs per SM;",
-      "copy-engine rows threshold 128 B instead of 256 B.  Shipping configuration: strided tiles on the 2-CTA build, everything else on the 3-CTA build, rows ≥ 256 B.", ""]
+      "copy-engine rows threshold 128 B instead of 256 B (A/B columns: all LSU modes on one build, 32 KiB transpose tiles with scalar shared-memory accesses).",
+      "Shipping configuration: strided tiles on the 2-CTA build, transpose tiles (16 KiB, conflict-free word layout) on the 6-CTA build, every other LSU mode on the 3-CTA build, rows ≥ 256 B.", ""]
 files = sorted(glob.glob(os.path.join(RAW, "r02_kernel_cases_*.jsonl")))
 cases = {}
 for fn in files:
