@@ -38,6 +38,8 @@ def _build_state(rank: int, world: int):
 
 def _worker(rank: int, world: int, store_path: str, root: str, use_ref: bool, mode: str):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["LOCAL_WORLD_SIZE"] = str(world)  # as torchrun sets it: ranks share the host-wide pool of I/O tokens
+    os.environ["TSNAP_B200_HOST_IO_TOKENS"] = "3"  # fewer tokens than workers: the semaphore path is exercised
     os.environ["TORCHSNAPSHOT_MAX_CHUNK_SIZE_BYTES_OVERRIDE"] = "8192"
     os.environ["TORCHSNAPSHOT_SLAB_SIZE_THRESHOLD_BYTES_OVERRIDE"] = "4096"
     dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)

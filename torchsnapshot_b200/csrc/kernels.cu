@@ -714,126 +714,11 @@ __device__ __forceinline__ void tile_transpose_t(const Member& m, uint32_t index
     }
 }
 
-// Common tile addressing of the transpose paths.
-struct TrTile {
-    const char* sp;
-    char* dp;
-    int64_t ssB, dsA;
-    uint32_t na, nb;
-};
-template <int kA, int kB>
-__device__ __forceinline__ TrTile transpose_tile(const Member& m, uint32_t index) {
-    const uint32_t A = m.shift & 255, B = (m.shift >> 8) & 255;
-    const uint64_t sA = (uint64_t)m.osize[A], sB = (uint64_t)m.osize[B];
-    const uint32_t tilesA = (uint32_t)((sA + kA - 1) / kA), tilesB = (uint32_t)((sB + kB - 1) / kB);
-    const uint32_t ib = index % tilesB;
-    uint32_t rest = index / tilesB;
-    const uint32_t ia = rest % tilesA;
-    rest /= tilesA;
-    int64_t so = 0, dofs = 0;
-    for (int i = (int)m.nouter - 1; i >= 0; --i) {
-        if ((uint32_t)i == A || (uint32_t)i == B) continue;
-        const uint32_t sz = (uint32_t)m.osize[i];
-        const uint32_t idx = rest % sz;
-        rest /= sz;
-        so += (int64_t)idx * m.sstride[i];
-        dofs += (int64_t)idx * m.dstride[i];
-    }
-    const uint64_t a0 = (uint64_t)ia * kA, b0 = (uint64_t)ib * kB;
-    TrTile t;
-    t.na = (uint32_t)(sA - a0 < (uint64_t)kA ? sA - a0 : kA);
-    t.nb = (uint32_t)(sB - b0 < (uint64_t)kB ? sB - b0 : kB);
-    t.ssB = m.sstride[B];
-    t.dsA = m.dstride[A];
-    t.sp = reinterpret_cast<const char*>(m.src) + so + (int64_t)a0 * m.sstride[A] + (int64_t)b0 * t.ssB;
-    t.dp = reinterpret_cast<char*>(m.dst) + dofs + (int64_t)a0 * t.dsA + (int64_t)b0 * m.dstride[B];
-    return t;
-}
-__device__ __forceinline__ bool transpose_tile_full(const TrTile& t, uint32_t kA, uint32_t kB) {
-    return t.na == kA && t.nb == kB && ((reinterpret_cast<uint64_t>(t.sp) | (uint64_t)t.ssB) & 15) == 0 &&
-           ((reinterpret_cast<uint64_t>(t.dp) | (uint64_t)t.dsA) & 15) == 0;
-}
-
-// Interior 64 x 64 tile of 4-byte elements.  Lane <-> source row b: every thread reads 64 contiguous bytes of its row
-// (4 x 16 B), stores the 16 words to the TRANSPOSED shared tile sT[a][b] (consecutive lanes -> consecutive words:
-// conflict-free), then rows of sT are read back with 16 B shared loads and written with 16 B global stores.
-__device__ __forceinline__ void transpose_full_4B(const TrTile& t, unsigned char* tbuf) {
-    constexpr int kPitch = 64 + 4;  // words; keeps rows 16 B aligned
-    uint32_t* sT = reinterpret_cast<uint32_t*>(tbuf);
-    const uint32_t b = threadIdx.x & 63, quarter = threadIdx.x >> 6;
-    const char* row = t.sp + (int64_t)b * t.ssB + quarter * 64;
-    uint4 r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) r[j] = ld_cached16(row + j * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t a = quarter * 16 + j * 4;
-        sT[(a + 0) * kPitch + b] = r[j].x;
-        sT[(a + 1) * kPitch + b] = r[j].y;
-        sT[(a + 2) * kPitch + b] = r[j].z;
-        sT[(a + 3) * kPitch + b] = r[j].w;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
-        const uint32_t a = idx >> 4, q = idx & 15;
-        const uint4 v = *reinterpret_cast<const uint4*>(sT + a * kPitch + q * 4);
-        st_stream16(t.dp + (int64_t)a * t.dsA + q * 16, v);
-    }
-}
-
-// Interior 128 (A) x 64 (B) tile of 2-byte elements.  Lane <-> source row PAIR (2p, 2p+1): 32 contiguous bytes of both
-// rows per thread; byte permutes interleave the two rows so that each 32-bit word of the transposed shared tile
-// sT[a][p] already holds the destination's neighbours (b = 2p, 2p+1): no sub-word shared-memory traffic at all.
-__device__ __forceinline__ void transpose_full_2B(const TrTile& t, unsigned char* tbuf) {
-    constexpr int kPitch = 32 + 4;  // words
-    uint32_t* sT = reinterpret_cast<uint32_t*>(tbuf);
-    const uint32_t p = threadIdx.x & 31, g = threadIdx.x >> 5;  // g: which 32 B of the 256 B rows
-    const char* row0 = t.sp + (int64_t)(2 * p) * t.ssB + g * 32;
-    const char* row1 = row0 + t.ssB;
-    uint4 r0[2], r1[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        r0[j] = ld_cached16(row0 + j * 16);
-        r1[j] = ld_cached16(row1 + j * 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const uint32_t w0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
-        const uint32_t w1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
-        const uint32_t a = g * 16 + j * 8;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            sT[(a + 2 * k) * kPitch + p] = __byte_perm(w0[k], w1[k], 0x5410);      // elements a+2k of rows 2p, 2p+1
-            sT[(a + 2 * k + 1) * kPitch + p] = __byte_perm(w0[k], w1[k], 0x7632);  // elements a+2k+1
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t idx = threadIdx.x + (uint32_t)k * kLsuThreads;
-        const uint32_t a = idx >> 3, q = idx & 7;
-        const uint4 v = *reinterpret_cast<const uint4*>(sT + a * kPitch + q * 4);
-        st_stream16(t.dp + (int64_t)a * t.dsA + q * 16, v);
-    }
-}
-
 __device__ __noinline__ void tile_transpose(const Member& m, uint32_t index, unsigned char* tbuf) {
     switch (m.unit) {  // geometry = plan.h transpose_side_a / transpose_side_b
         case 8: tile_transpose_t<uint64_t, 64, 32>(m, index, tbuf); break;
-        case 4: {
-            const TrTile t = transpose_tile<64, 64>(m, index);
-            if (transpose_tile_full(t, 64, 64)) transpose_full_4B(t, tbuf);
-            else tile_transpose_t<uint32_t, 64, 64>(m, index, tbuf);
-            break;
-        }
-        case 2: {
-            const TrTile t = transpose_tile<128, 64>(m, index);
-            if (transpose_tile_full(t, 128, 64)) transpose_full_2B(t, tbuf);
-            else tile_transpose_t<uint16_t, 128, 64>(m, index, tbuf);
-            break;
-        }
+        case 4: tile_transpose_t<uint32_t, 64, 64>(m, index, tbuf); break;
+        case 2: tile_transpose_t<uint16_t, 128, 64>(m, index, tbuf); break;
         default: tile_transpose_t<uint8_t, 128, 128>(m, index, tbuf); break;
     }
 }
@@ -989,7 +874,7 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kLsuThreads, kMinBlocks) tsnap_lsu_copy_kernel(const Member* __restrict__ members,
                                                                             const Tile* __restrict__ tiles, uint32_t ntiles) {
     __shared__ Member sm;
-    __shared__ __align__(16) unsigned char tbuf[128 * 36 * 4];  // transpose tile: 128 x 36 words (2-byte path) >= 64 x 68 words, 64 x 65 x 4 B, 32 x 65 x 8 B, 128 x 129 B
+    __shared__ __align__(16) unsigned char tbuf[64 * 65 * 4 + 64];  // transpose tile: 64 x 65 x 4 B >= 64 x 129 x 2 B, 32 x 65 x 8 B, 128 x 129 B
     uint32_t loaded = 0xffffffffu;
     Tile next = blockIdx.x < ntiles ? tiles[blockIdx.x] : Tile{0, 0};
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
