@@ -197,6 +197,7 @@ typedef struct tsnap_job_stats {
     uint64_t bytes_rows;        /* logical bytes moved run by run by the rows (TMA) kernel   */
     uint64_t n_tiles_rows;
     double kernel_rows_ms;
+    uint64_t max_slots_in_flight; /* peak number of ring slots the job held at once (host-memory footprint / slot size) */
     double link_starved_ms;     /* part of slot_wait_ms during which NO payload copy was queued or running on the copy
                                    stream: the link really idled for want of a pinned slot (slot_wait_ms alone also
                                    counts waits behind a full queue of copies, which cost nothing)            */
@@ -218,6 +219,11 @@ typedef struct tsnap_arena_hint {
 } tsnap_arena_hint;
 int tsnap_job_arena_hint(tsnap_job* job, tsnap_arena_hint* out);
 int tsnap_job_set_arena(tsnap_job* job, void* device_ptr, uint64_t nbytes);
+
+/* Host-memory budget of a job (T:scheduler.py:47-67, 257-272: the reference admits staging while the per-rank budget
+ * allows).  The engine's host footprint is its pinned ring; a job never holds more than max(2, bytes / slot size) ring
+ * slots at a time (filled by the link and not yet written, or read and not yet uploaded).  0 = no limit beyond the ring. */
+int tsnap_job_set_host_budget(tsnap_job* job, uint64_t bytes);
 
 /* ---- timeline of a finished job (engines created with TSNAP_ENGINE_TRACE) ------------------------
  * One record per pipeline event; times are milliseconds since submit on the host's monotonic clock.

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.EngineConfig) == 32
     assert ctypes.sizeof(_native.TraceRec) == 40
     assert ctypes.sizeof(_native.ArenaHint) == 32
-    assert ctypes.sizeof(_native.JobStats) == 27 * 8
+    assert ctypes.sizeof(_native.JobStats) == 28 * 8
 
 
 def test_device_engine_fails_loudly_without_gpu():

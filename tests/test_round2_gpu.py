@@ -412,3 +412,20 @@ def test_cast_and_quantize_on_save_on_gpu(tmp_path):
         snap.restore({"m": tgt})
         _, scale, _ = hook.tsnap_quant("m/w", w)
         assert (tgt["w"] - w).abs().max().item() <= scale * 0.5 + 1e-6 and torch.equal(tgt["i"], st["i"])
+
+
+def test_host_memory_budget_bounds_the_ring_slots_in_flight(tmp_path, fresh_engines, monkeypatch):
+    """TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES (T:scheduler.py:47-58) is honoured by the native path: a job never
+    holds more pinned slots than the budget allows, and the snapshot is still bit-exact."""
+    os.environ["TSNAP_B200_PINNED_SLOT_BYTES"] = str(1 << 20)
+    os.environ["TSNAP_B200_PINNED_SLOTS"] = "32"
+    monkeypatch.setenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES", str(6 << 20))
+    state = {f"p{i}": det_tensor((4 << 20,), torch.float32, i).to(DEV) for i in range(4)}  # 64 MiB
+
+    def bounded(st):
+        assert 1 <= st["max_slots_in_flight"] <= 6, st["max_slots_in_flight"]
+
+    _save_and_check(tmp_path, "s", state, bounded)
+    monkeypatch.delenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES")
+    st = _save_and_check(tmp_path, "t", state)
+    assert st["max_slots_in_flight"] > 6  # without the budget the ring is used freely

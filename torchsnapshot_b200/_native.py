@@ -124,6 +124,7 @@ class JobStats(C.Structure):
         ("bytes_rows", C.c_uint64),
         ("n_tiles_rows", C.c_uint64),
         ("kernel_rows_ms", C.c_double),
+        ("max_slots_in_flight", C.c_uint64),
         ("link_starved_ms", C.c_double),
     ]
 
@@ -203,6 +204,7 @@ EXPORTED_SYMBOLS = [
     "tsnap_job_get_trace",
     "tsnap_engine_probe",
     "tsnap_scatter_device",
+    "tsnap_job_set_host_budget",
 ]
 
 
@@ -248,6 +250,7 @@ def _load() -> C.CDLL:
     lib.tsnap_job_get_trace.argtypes = [vp, C.POINTER(TraceRec), C.c_uint64, C.POINTER(C.c_uint64)]
     lib.tsnap_engine_probe.argtypes = [vp, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_double)]
     lib.tsnap_scatter_device.argtypes = [vp, vp, C.c_uint64, C.POINTER(CopyDesc), C.c_int32, vp]
+    lib.tsnap_job_set_host_budget.argtypes = [vp, C.c_uint64]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tsnap_last_error", "tsnap_dtype_size"):
@@ -425,6 +428,10 @@ class Job:
             return
         check(lib.tsnap_job_set_arena(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size()))
         self._arena = tensor
+
+    def set_host_budget(self, nbytes: int) -> None:
+        """Host-memory budget of this job (T:scheduler.py:47-67): bounds the pinned ring slots it holds at once."""
+        check(lib.tsnap_job_set_host_budget(self._h, max(0, int(nbytes))))
 
     def _provision_arena(self) -> None:
         """HBM staging comes from PyTorch's caching allocator, so it is visible to — and reusable by — the training job

@@ -468,6 +468,23 @@ void tsnap_job::add_trace(int kind, int lane, int file, double t0, double t1, ui
     std::lock_guard<std::mutex> g(trace_mu);
     trace.push_back(tsnap_trace_rec{kind, lane, file, 0, t0, t1, bytes});
 }
+char* tsnap_job::take_slot() {
+    {
+        std::unique_lock<std::mutex> g(slot_mu);
+        slot_cv.wait(g, [this] { return max_slots <= 0 || slots_held < max_slots; });
+        ++slots_held;
+        slots_peak = std::max(slots_peak, slots_held);
+    }
+    return eng->ring.acquire();
+}
+void tsnap_job::give_slot(char* p) {
+    eng->ring.release(p);
+    {
+        std::lock_guard<std::mutex> g(slot_mu);
+        --slots_held;
+    }
+    slot_cv.notify_one();
+}
 bool tsnap_job::failed() {
     std::lock_guard<std::mutex> g(mu);
     return err_code != 0;
@@ -1176,7 +1193,7 @@ static int run_save_inner(tsnap_job* job) {
             auto tw = clk::now();
             const double tw_ms = eng->trace ? job->now_ms() : 0;
             const bool link_idle = job->copies_in_flight.load(std::memory_order_acquire) == 0;
-            char* slot = eng->ring.acquire();
+            char* slot = job->take_slot();
             const double waited = ms_since(tw);
             job->slot_wait_us += int64_t(waited * 1000.0);
             if (link_idle) job->link_starved_us += int64_t(waited * 1000.0);
@@ -1222,7 +1239,7 @@ static int run_save_inner(tsnap_job* job) {
                         job->io_busy_us += int64_t(ms_since(tb) * 1000.0);
                         if (eng->trace) job->add_trace(TSNAP_TR_PWRITE, g_lane, fidx, t0w, job->now_ms(), n);
                     }
-                    eng->ring.release(slot);
+                    job->give_slot(slot);
                     finish_file_part(job, *fp, n, true);
                 });
             });
@@ -1328,7 +1345,7 @@ static int run_load_inner(tsnap_job* job) {
             char* base = w->direct ? nullptr : job->arena + w->region_off + f->arena_off;
             for (uint64_t lo = 0; lo < f->nbytes; lo += sb) {
                 const uint64_t n = std::min(sb, f->nbytes - lo);
-                char* slot = eng->ring.acquire();
+                char* slot = job->take_slot();
                 post_slot(eng, slot, [eng, job, w, wi, f, fi, base, slot, lo, n, shared, last_wave] {
                     NvtxRange nvtx_r("tsnap:pread chunk + H2D enqueue");
                     cudaSetDevice(eng->device);
@@ -1376,7 +1393,7 @@ static int run_load_inner(tsnap_job* job) {
                             job->add_trace(TSNAP_TR_H2D, 0, fi, std::max(t_issue, job->last_copy_done_ms), t1, n);
                             job->last_copy_done_ms = t1;
                         }
-                        eng->ring.release(slot);
+                        job->give_slot(slot);
                         finish_file_part(job, *f, n, false);
                     });
                     // the worker that enqueues the last upload of the wave launches its scatter kernels
@@ -1943,6 +1960,10 @@ int tsnap_job_get_stats(tsnap_job* job, tsnap_job_stats* out) {
     job->stats.io_queue_ms = job->io_queue_us.load() / 1000.0;
     job->stats.n_memcpy = uint64_t(job->n_memcpy.load());
     job->stats.link_starved_ms = job->link_starved_us.load() / 1000.0;
+    {
+        std::lock_guard<std::mutex> gs(job->slot_mu);
+        job->stats.max_slots_in_flight = uint64_t(job->slots_peak);
+    }
     *out = job->stats;
     return TSNAP_OK;
 }
@@ -2005,6 +2026,14 @@ int tsnap_job_set_arena(tsnap_job* job, void* device_ptr, uint64_t nbytes) {
     job->arena = static_cast<char*>(device_ptr);
     job->arena_bytes = nbytes / 512 * 512;  // two equal 256 B-aligned halves
     job->arena_set = true;
+    return TSNAP_OK;
+}
+
+int tsnap_job_set_host_budget(tsnap_job* job, uint64_t bytes) {
+    if (!job) return set_err(TSNAP_EINVAL, "null job");
+    if (job->submitted) return set_err(TSNAP_ESTATE, "job already submitted");
+    const uint64_t sb = job->eng->cfg.pinned_slot_bytes ? job->eng->cfg.pinned_slot_bytes : (32ull << 20);
+    job->max_slots = bytes ? int(std::max<uint64_t>(2, std::min<uint64_t>(bytes / sb, 1u << 20))) : 0;
     return TSNAP_OK;
 }
 

@@ -225,6 +225,13 @@ struct tsnap_job {
     bool timing_collected = false;
     std::atomic<int64_t> slot_wait_us{0}, io_busy_us{0}, io_queue_us{0}, n_memcpy{0}, link_starved_us{0};
     std::atomic<int> copies_in_flight{0};  // payload chunks issued on s_copy and not yet retired
+    // host-memory budget: ring slots this job may hold at once (0 = unlimited)
+    int max_slots = 0;
+    int slots_held = 0, slots_peak = 0;
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
+    char* take_slot();             // blocks on the budget, then on the ring
+    void give_slot(char* p);
     std::chrono::steady_clock::time_point t_submit;
 
     void fail(int code, const std::string& msg);

@@ -96,9 +96,11 @@ class _NativeJobs:
             self.jobs[key] = j
         return j
 
-    def submit(self) -> None:
+    def submit(self, memory_budget_bytes: int = 0) -> None:
         for key, j in self.jobs.items():
             stream = torch.cuda.current_stream(key).cuda_stream if key >= 0 else None
+            # the per-rank host-memory budget (T:scheduler.py:47-67) bounds the pinned slots a job holds at once
+            j.set_host_budget(memory_budget_bytes // max(1, len(self.jobs)))
             j.submit(stream)
 
     def wait_device(self) -> None:
@@ -198,7 +200,7 @@ async def execute_write_reqs(
             generic.append(wr)
     lap("describe+build_job")
     if native is not None:
-        native.submit()
+        native.submit(memory_budget_bytes)
     lap("submit")
 
     # generic pipeline: budget-gated staging, bounded concurrent writes
@@ -433,7 +435,7 @@ async def execute_read_reqs(
         total += hi - lo
     try:
         if native is not None:
-            native.submit()
+            native.submit(memory_budget_bytes)
         if candidates:
             LAST_STATS["read_once"] = {"ranges": len(candidates), "bytes": sum(k[2] - k[1] for k, _, _ in candidates),
                                        "bytes_read_by_this_rank": _execute_shared_reads(shared_pg, root, candidates, owner)}

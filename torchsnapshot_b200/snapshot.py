@@ -84,10 +84,10 @@ class Snapshot:
         cls._validate_app_state(app_state)
         loop = asyncio.new_event_loop()
         pgw = PGWrapper(pg)
-        path, globs = cls._coalesce_path_and_replicated(path, pgw, app_state, replicated or [])
+        path, globs, keys = cls._coalesce_path_and_replicated(path, pgw, app_state, replicated or [])
         storage = url_to_storage_plugin_in_event_loop(path, loop, storage_options)
         try:
-            pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, False, _custom_tensor_prepare_func)
+            pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, False, _custom_tensor_prepare_func, keys)
             # the engine is draining in its own threads: encode the metadata meanwhile (json with indent=2
             # runs in the pure-Python encoder, ~40 ms for a 300-entry manifest)
             encoded = metadata.to_yaml().encode("utf-8") if pgw.get_rank() == 0 else None
@@ -118,10 +118,10 @@ class Snapshot:
         cls._validate_app_state(app_state)
         loop = asyncio.new_event_loop()
         pgw = PGWrapper(pg)
-        path, globs = cls._coalesce_path_and_replicated(path, pgw, app_state, replicated or [])
+        path, globs, keys = cls._coalesce_path_and_replicated(path, pgw, app_state, replicated or [])
         storage = url_to_storage_plugin_in_event_loop(path, loop, storage_options)
         try:
-            pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, True, _custom_tensor_prepare_func)
+            pending, metadata = cls._take_impl(path, app_state, globs, pgw, storage, loop, True, _custom_tensor_prepare_func, keys)
         except BaseException:
             storage.sync_close(loop)
             loop.close()
@@ -139,6 +139,7 @@ class Snapshot:
         loop: asyncio.AbstractEventLoop,
         is_async_snapshot: bool,
         _custom_tensor_prepare_func: Optional[CustomPrepareFunc],
+        global_keys: Optional[List[str]] = None,
     ) -> Tuple[PendingIOWork, SnapshotMetadata]:
         import gc
         import time as _time
@@ -150,13 +151,13 @@ class Snapshot:
         gc_was_enabled = gc.isenabled()
         gc.disable()
         try:
-            return cls._take_impl_nogc(path, app_state, replicated, pgw, storage, loop, is_async_snapshot, _custom_tensor_prepare_func, LAST_STATS, _time)
+            return cls._take_impl_nogc(path, app_state, replicated, pgw, storage, loop, is_async_snapshot, _custom_tensor_prepare_func, LAST_STATS, _time, global_keys)
         finally:
             if gc_was_enabled:
                 gc.enable()
 
     @classmethod
-    def _take_impl_nogc(cls, path, app_state, replicated, pgw, storage, loop, is_async_snapshot, _custom_tensor_prepare_func, LAST_STATS, _time):
+    def _take_impl_nogc(cls, path, app_state, replicated, pgw, storage, loop, is_async_snapshot, _custom_tensor_prepare_func, LAST_STATS, _time, global_keys=None):
         phases: Dict[str, float] = {}
         _t = [_time.perf_counter()]
 
@@ -178,7 +179,9 @@ class Snapshot:
             manifest.update(m)
             flattened.update(f)
         rank = pgw.get_rank()
-        global_keys = cls._gather_keys(list(app_state.keys()), pgw)
+        # the keys of all ranks normally travel with the path/glob exchange of this take (one collective less)
+        if global_keys is None:
+            global_keys = cls._gather_keys(list(app_state.keys()), pgw)
         lap("gather_keys")
         for key in global_keys:
             if key in app_state:
@@ -389,16 +392,18 @@ class Snapshot:
         return sorted(set(itertools.chain.from_iterable(gathered)))
 
     @classmethod
-    def _coalesce_path_and_replicated(cls, path: str, pgw: PGWrapper, app_state: AppState, replicated: List[str]) -> Tuple[str, Set[str]]:
+    def _coalesce_path_and_replicated(cls, path: str, pgw: PGWrapper, app_state: AppState, replicated: List[str]) -> Tuple[str, Set[str], List[str]]:
         # one exchange carries the path (rank 0's wins, T:snapshot.py:871-877) and the replication globs
         # (T:snapshot.py:880-887); the reference spends a broadcast and an all-gather on them
         globs = cls._infer_replicated(replicated, app_state)
         everyone: List[Any] = [None] * pgw.get_world_size()
-        pgw.all_gather_object(everyone, (path, globs))
+        # ... and the app_state keys of every rank (T:snapshot.py:921-927 spends another all-gather on them)
+        keys = [k for k, v in app_state.items() if not isinstance(v, RNGState)]  # RNG state is handled apart, like in _take_impl
+        pgw.all_gather_object(everyone, (path, globs, keys))
         chosen = everyone[0][0]
         if chosen != path:
             logger.warning(f"Rank {pgw.get_rank()} specified a path ({path}) different from rank 0 ({chosen}). Using path specified by rank 0.")
-        return chosen, cls._coalesce_replicated([g for _, g in everyone])
+        return chosen, cls._coalesce_replicated([e[1] for e in everyone]), sorted(set(itertools.chain.from_iterable(e[2] for e in everyone)))
 
     @staticmethod
     def _coalesce_replicated(global_replicated: List[List[str]]) -> Set[str]:
