@@ -73,6 +73,22 @@ if world >= 2 and rank < world // 2:
     snap = B.Snapshot(os.path.join(root, "sync"))
     got = snap.read_object("0/extra/table", obj_out=dst.new_zeros(rows, 96))
     assert torch.equal(got.cpu(), full)
+# a replicated payload file goes missing: the restore must FAIL ON EVERY RANK (with read-once only one rank reads the file;
+# its error is propagated instead of leaving the peers with garbage or hanging in the broadcast)
+path = os.path.join(root, "sync")
+dist.barrier(device_ids=[local])
+if rank == 0:
+    meta = json.load(open(os.path.join(path, ".snapshot_metadata")))["manifest"]
+    victim = meta["0/model/module.0.weight"]["location"]
+    os.remove(os.path.join(path, victim))
+dist.barrier(device_ids=[local])
+m3 = torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 512)).to(dev)
+failed = False
+try:
+    B.Snapshot(path).restore({"model": DDP(m3, device_ids=[local])})
+except Exception as e:
+    failed = True
+assert failed, "a missing replicated file must fail the restore on every rank"
 print(f"rank {rank}: multi-GPU check OK", flush=True)
 dist.barrier(device_ids=[local])
 if rank == 0: shutil.rmtree(root, ignore_errors=True)

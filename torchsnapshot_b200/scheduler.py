@@ -350,12 +350,16 @@ def _execute_shared_reads(pg: PGWrapper, root: str, shared: List[Tuple[Tuple[str
                 job.add_member(fi, _native.load_desc(buf[off : off + (hi - lo)], 0), buf)
                 read_bytes += hi - lo
         job.submit(torch.cuda.current_stream(dev).cuda_stream)
+    err: Optional[BaseException] = None
     try:
         waited = False
         for i, (r, nb, members) in enumerate(plan):
             if r == rank:
                 if not waited:
-                    job.wait()
+                    try:
+                        job.wait()
+                    except Exception as e:  # keep taking part in the exchange: the peers are already waiting in it
+                        err = e
                     waited = True
                 buf = mine[i]
             else:
@@ -365,8 +369,19 @@ def _execute_shared_reads(pg: PGWrapper, root: str, shared: List[Tuple[Tuple[str
             for key, off in members:
                 descs += _shift_descs(by_key[key][0], off)
             # ordered after the broadcast on the current stream; synchronous, so `buf` may be dropped afterwards
-            eng.scatter_device(buf, descs, stream=torch.cuda.current_stream(dev).cuda_stream)
+            if err is None:
+                try:
+                    eng.scatter_device(buf, descs, stream=torch.cuda.current_stream(dev).cuda_stream)
+                except Exception as e:
+                    err = e
             mine.pop(i, None)
+        # a read error on one rank must fail the restore on every rank (each rank would have hit it reading for itself)
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=f"cuda:{dev}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=pg.pg)
+        if err is not None:
+            raise err
+        if int(flag.item()):
+            raise RuntimeError("read-once restore: a peer rank failed to read or scatter a replicated byte range (see its log)")
     finally:
         if job is not None:
             job.destroy()
