@@ -79,7 +79,8 @@ path = os.path.join(root, "sync")
 dist.barrier(device_ids=[local])
 if rank == 0:
     meta = json.load(open(os.path.join(path, ".snapshot_metadata")))["manifest"]
-    victim = meta["0/model/module.0.weight"]["location"]
+    ent = meta["0/model/module.0.weight"]  # a plain tensor entry, or chunked by the partitioner at larger world sizes
+    victim = ent["location"] if "location" in ent else ent["chunks"][0]["tensor"]["location"]
     os.remove(os.path.join(path, victim))
 dist.barrier(device_ids=[local])
 m3 = torch.nn.Sequential(torch.nn.Linear(1024, 1024), torch.nn.ReLU(), torch.nn.Linear(1024, 512)).to(dev)
