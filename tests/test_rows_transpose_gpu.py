@@ -88,6 +88,47 @@ def test_tiled_transpose(dtype):
     _roundtrip(views, any_mode)
 
 
+def _tma_tiles(sa, sb, esz):
+    """tile count of the tensor-map transpose: 32 KiB tiles, the shape variant that pads (sa, sb) least (plan.h)."""
+    a0, b0 = (128 if esz == 2 else 64), (64 if esz == 8 else 128)
+    return min(-(-sa // a) * -(-sb // b) for a, b in ((a0, b0), (a0 * 2, b0 // 2), (a0 // 2, b0 * 2)))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int32, torch.bfloat16, torch.float16, torch.int16, torch.float64, torch.int64])
+def test_tma_transpose_every_tile_shape_and_edges(dtype, monkeypatch):
+    """2-D transposes whose strides are 16 B multiples run on the tensor-map TMA kernel: every (element size, tile shape)
+    instantiation, clipped edge tiles on both extents, both directions; the LSU transpose is the A/B and the fallback."""
+    esz = torch.empty((), dtype=dtype).element_size()
+    a0, b0 = (128 if esz == 2 else 64), (64 if esz == 8 else 128)
+    lsu_a, lsu_b = (64 if esz >= 4 else 128), (32 if esz == 8 else 64)
+    # (rows, cols) of the dense source; the staged view is its .t(): logical (cols, rows), A = dim 0 (extent cols), B = dim 1
+    shapes = [(4096, 2048), (4096, a0 // 2), (b0 // 2, 4096), (4096, a0), (b0, 4096), (1000, 1000 + 16 // esz * 3), (520, 264)]
+    for seed, (r, c) in enumerate(shapes):
+        v = det_tensor((r, c), dtype, 20 + seed).to(DEV).t()
+        counts = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("TSNAP_B200_TMA_TRANSPOSE", flag)
+            counts[flag] = _roundtrip([v], lambda st: None)["n_tiles_lsu"]
+        assert counts["1"] == _tma_tiles(c, r, esz), (dtype, (r, c), counts)
+        assert counts["0"] == -(-c // lsu_a) * -(-r // lsu_b), (dtype, (r, c), counts)
+
+
+def test_tma_transpose_higher_rank_and_fallbacks(monkeypatch):
+    """3/4/5-D permutes go through rank-5 tensor maps; 6 dims, 1-byte elements, odd strides or bases stay on the LSU path —
+    all byte-identical to the oracle, in one packed image."""
+    monkeypatch.setenv("TSNAP_B200_TMA_TRANSPOSE", "1")
+    c3 = det_tensor((5, 136, 72), torch.float32, 31).to(DEV)
+    c4 = det_tensor((3, 4, 264, 40), torch.bfloat16, 32).to(DEV)
+    c5 = det_tensor((2, 3, 2, 72, 24), torch.float64, 33).to(DEV)
+    c6 = det_tensor((2, 2, 2, 2, 40, 24), torch.float32, 34).to(DEV)
+    odd = det_tensor((257, 1037), torch.float32, 35).to(DEV)
+    byt = det_tensor((300, 400), torch.uint8, 36).to(DEV)
+    views = [c3.permute(0, 2, 1), c3.permute(2, 0, 1), c3.transpose(0, 2), c4.permute(0, 3, 1, 2), c4.permute(1, 0, 3, 2), c4.transpose(1, 3),
+             c5.permute(0, 1, 2, 4, 3), c5.permute(4, 1, 2, 0, 3), c6.permute(0, 1, 2, 3, 5, 4), odd.t(), odd[1:, 4:].t(), byt.t(),
+             c3.permute(0, 2, 1)[1:4, 8:64, 16:120]]
+    _roundtrip(views, lambda st: None)
+
+
 def test_transpose_and_rows_through_snapshot_api(tmp_path):
     import torchsnapshot_b200 as B
     from tests.util import wire_bytes

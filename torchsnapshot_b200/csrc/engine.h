@@ -172,6 +172,8 @@ struct Wave {
     uint64_t region_off = 0;  // offset of the region inside the arena
     std::vector<Member> members;
     std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu, tiles_strided, tiles_transpose;  // the last two run their own builds of the LSU kernel
+    std::vector<Tile> tiles_tma;    // kModeTransposeTma
+    std::vector<TmaPair> tmaps;     // their tensor maps (Member.q_zero_point indexes this table)
     void* d_tables = nullptr;
     size_t table_bytes = 0, table_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_kr = nullptr, ev_k2 = nullptr;  // kernel timing: bulk | rows | lsu

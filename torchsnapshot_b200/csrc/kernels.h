@@ -18,4 +18,14 @@ cudaError_t launch_rows(const Member* d_members, const Tile* d_tiles, uint32_t n
 enum LsuVariant { kLsuDefault = 0, kLsuStrided = 1, kLsuTranspose = 2 };
 cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
                        cudaStream_t stream, int variant);
+
+// kModeTransposeTma (transpose_tma.cu): tensor-map TMA tile loads/stores around a register block transposition.
+// make_tma_pair encodes the two tensor maps of a kModeTranspose member (false: the member stays on the LSU transpose —
+// 1-byte elements, bases or strides that are not 16 B multiples, more than 3 extra dims, TSNAP_B200_TMA_TRANSPOSE=0,
+// or a driver without cuTensorMapEncodeTiled).
+bool transpose_tma_enabled();
+bool make_tma_pair(const Member& m, TmaPair* out, uint32_t* variant);  // variant = tile shape, for Member.shift bits 16-17
+cudaError_t init_transpose_tma();
+cudaError_t launch_transpose_tma(const Member* d_members, const Tile* d_tiles, const TmaPair* d_maps, uint32_t ntiles, int sm_count,
+                                 cudaStream_t stream);
 }  // namespace tsnap

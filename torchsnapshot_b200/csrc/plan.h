@@ -17,6 +17,11 @@
 namespace tsnap {
 
 constexpr int kMaxOuter = 8;
+#ifdef __CUDACC__
+#define TSNAP_HD __host__ __device__
+#else
+#define TSNAP_HD
+#endif
 constexpr uint32_t kTileBulk = 192 * 1024;  // bytes of one bulk (TMA) tile: a multiple of every ring stage size
 constexpr uint32_t kTileLsu = 128 * 1024;  // logical dst bytes of one LSU tile (per-tile setup costs ~2 dependent global round trips)
 constexpr uint64_t kBulkMin = 1024;        // contiguous runs shorter than this stay on the LSU path
@@ -28,6 +33,9 @@ enum Mode : uint32_t {
     kModeCast = 3,     // element-wise dtype conversion, strided both sides
     kModeTranspose = 5,  // no run is contiguous on both sides, but each side has a unit-stride dimension (a.t(), permute):
                          // shared-memory tiled transpose over those two dims, coalesced on both sides
+    kModeTransposeTma = 6,  // kModeTranspose whose bases and strides are 16 B multiples and whose elements are 2, 4 or 8
+                            // bytes: tensor-map TMA tile loads -> 16 B-block transposition in registers -> TMA tile stores
+                            // (transpose_tma.cu); chosen per wave by the engine, which owns the tensor maps
     kModeRows = 4,     // kModeStrided whose runs, strides and bases are all multiples of 16 B and whose runs are long
                        // enough for the copy engine: one cp.async.bulk per run (or one per stage on a dense side)
 };
@@ -55,7 +63,30 @@ struct alignas(16) Member {
     int64_t dstride[kMaxOuter];  // bytes
     double q_scale;              // kModeCast to TSNAP_QINT8/QUINT8: affine quantisation parameters; when `shift` bit 0
     int64_t q_zero_point;        // is set the tile holding the last element appends the 16-byte trailer at dst + bytes
+                                 // kModeTransposeTma: index of the member's TmaPair in the wave's tensor-map table
 };
+
+// Two CUtensorMap objects (128 B each, 64 B-aligned) of one kModeTransposeTma member, both of rank 5:
+// src dims {A, B, o0, o1, o2}, dst dims {B, A, o0, o1, o2} (o* = the remaining dims, highest index first, padded with 1)
+struct alignas(64) TmaPair {
+    unsigned char src[128];
+    unsigned char dst[128];
+};
+constexpr uint32_t kTmaTileBytes = 32 * 1024;  // payload of one kModeTransposeTma tile
+constexpr int kTmaMaxOther = 3;                // dims besides A and B a rank-5 tensor map can carry
+// elements per tile along A / B: 32 KiB, both sides >= 8 x 16 B vectors (conflict-free shared-memory block transposition)
+// and <= 256 elements (TMA box limit).  Variant (Member.shift bits 16-17): 0 square-ish, 1 twice as long along A,
+// 2 twice as long along B — the engine picks the one that pads the member's two extents least.
+constexpr uint32_t kTmaVariantShift = 16, kTmaVariants = 3;
+TSNAP_HD inline uint32_t transpose_tma_side_a(uint32_t esz, uint32_t variant) {
+    const uint32_t a = esz == 2 ? 128 : 64;
+    return variant == 1 ? a * 2 : variant == 2 ? a / 2 : a;
+}
+TSNAP_HD inline uint32_t transpose_tma_side_b(uint32_t esz, uint32_t variant) {
+    const uint32_t b = esz == 8 ? 64 : 128;
+    return variant == 1 ? b / 2 : variant == 2 ? b * 2 : b;
+}
+TSNAP_HD inline uint32_t transpose_tma_variant_of(uint32_t shift) { return (shift >> kTmaVariantShift) & 3; }
 
 struct Tile {
     uint32_t member;  // index into the member table of the same kernel
@@ -73,8 +104,11 @@ inline uint32_t transpose_side_b(uint32_t esz) { return esz == 8 ? 32 : esz == 1
 // number of tiles a member needs
 inline uint64_t tile_count(const Member& m) {
     if (m.bytes == 0) return 0;
-    if (m.mode == kModeTranspose) {
-        const uint32_t a = m.shift & 255, b = (m.shift >> 8) & 255, sa = transpose_side_a(m.unit), sb = transpose_side_b(m.unit);
+    if (m.mode == kModeTranspose || m.mode == kModeTransposeTma) {
+        const bool tma = m.mode == kModeTransposeTma;
+        const uint32_t a = m.shift & 255, b = (m.shift >> 8) & 255;
+        const uint32_t var = transpose_tma_variant_of(m.shift);
+        const uint32_t sa = tma ? transpose_tma_side_a(m.unit, var) : transpose_side_a(m.unit), sb = tma ? transpose_tma_side_b(m.unit, var) : transpose_side_b(m.unit);
         uint64_t n = 1;
         for (uint32_t i = 0; i < m.nouter; ++i)
             n *= i == a ? (uint64_t(m.osize[i]) + sa - 1) / sa : i == b ? (uint64_t(m.osize[i]) + sb - 1) / sb : uint64_t(m.osize[i]);
