@@ -65,6 +65,28 @@ def test_rows_kernel_column_shards_and_boxes():
     _roundtrip(views, rows)
 
 
+def test_rows_tma_boxes_match_the_per_run_kernel(monkeypatch):
+    """Runs of at most 1 KiB move as tensor-map boxes of many runs (clipped at the member's edge); longer runs, 5 outer dims
+    or TSNAP_B200_TMA_ROWS=0 stay on the per-run kernel — same bytes either way, both directions."""
+    base = det_tensor((5000, 512), torch.float32, 11).to(DEV)          # 2 KiB rows
+    deep = det_tensor((3, 2, 3, 2, 37, 96), torch.float32, 12).to(DEV)   # 384 B rows
+    views = [
+        base[:, 64:128],            # 256 B runs: 128-run boxes, 5000 = 39 x 128 + 8 (a clipped last box)
+        base[7:4001, 128:400],      # 1088 B runs: above the crossover, one request per run
+        base[:, :],                 # dense: bulk kernel, not a rows member
+        base[::3, 0:512:1][:, 256:],  # stepped rows, 1 KiB runs
+        deep[::2, :, ::2, 1, 2:35, 16:80],     # 256 B runs under 4 outer dims that do not merge: a rank-5 tensor map
+        deep[::2, :, ::2, :, 2:35, 16:80],     # 5 outer dims: more than a tensor map carries, per-run kernel
+        deep[1:, :, 1:, :, :, 32:96].transpose(0, 2),
+    ]
+    stats = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TSNAP_B200_TMA_ROWS", flag)
+        stats[flag] = _roundtrip(views, lambda st: None)
+    assert stats["1"]["bytes_rows"] == stats["0"]["bytes_rows"] > 0
+    assert stats["1"]["n_tiles_rows"] != stats["0"]["n_tiles_rows"], stats  # boxes vs 192 KiB tiles of runs
+
+
 def test_rows_kernel_declines_short_or_unaligned_runs():
     base = det_tensor((2048, 256), torch.float32, 4).to(DEV)
     views = [base[:, 4:36], base[:, 1:129]]  # 128 B runs (too short); 512 B runs starting 4 B off 16 B alignment

@@ -1,5 +1,6 @@
-"""The two transposes side by side — tensor-map TMA kernel (default) vs the LSU tiled transpose (TSNAP_B200_TMA_TRANSPOSE=0) —
-through the C-ABI stager seam: CUDA-event kernel time per case, the staged image checked against `.contiguous()`.
+"""The tensor-map TMA kernels against the kernels they replace, through the C-ABI stager seam: transposes (TMA tile kernel vs
+the LSU tiled transpose, TSNAP_B200_TMA_TRANSPOSE=0) and short-run column shards (one TMA box of many runs vs one copy-engine
+request per run, TSNAP_B200_TMA_ROWS=0).  CUDA-event kernel time per case, the staged image checked against `.contiguous()`.
 
     python tools/transpose_tune.py [--reps 3] [--cases a,b] > gpurun_out/transpose_cases.jsonl
 """
@@ -36,6 +37,11 @@ def cases():
     n = (1 << 20) + 64
     yield "fp32_Nx64_tall", base[: n * 64].view(n, 64).t(), False
     yield "fp32_64xN_wide", base[: n * 64].view(64, n).t(), False
+    # column shards: runs of 256 B .. 2 KiB out of rows twice as long (256 MiB of payload each)
+    for run in (256, 512, 1024, 2048):
+        rows = (512 << 20) // (2 * run)
+        yield f"rows_{run}B_runs", base[: rows * 2 * run // 4].view(rows, 2 * run // 4)[:, run // 8 : run // 8 + run // 4], run == 512
+    yield "rows_3d_272B_runs", base[: 50 * 1000 * 200].view(50, 1000, 200)[3:47, 5:990, 64:132], True  # 272 B runs, clipped boxes
 
 
 for name, t, verify in cases():
@@ -45,6 +51,7 @@ for name, t, verify in cases():
     want = t.contiguous().view(torch.uint8).reshape(-1).cpu() if verify else None
     for mode in args.modes.split(","):
         os.environ["TSNAP_B200_TMA_TRANSPOSE"] = mode
+        os.environ["TSNAP_B200_TMA_ROWS"] = mode
         desc = [N.save_desc(t, 0)]
         best, ok = None, None
         for rep in range(args.reps + 1):
@@ -56,6 +63,6 @@ for name, t, verify in cases():
             sb.release()
             if rep and (best is None or st["kernel_ms"] < best):
                 best = st["kernel_ms"]
-        print(json.dumps({"case": name, "kernel": "tma" if mode != "0" else "lsu", "kernel_ms": round(best, 4), "gbs": round(2 * nbytes / 1e6 / best, 1),
+        print(json.dumps({"case": name, "kernel": "tma" if mode != "0" else ("per-run" if name.startswith("rows") else "lsu"), "kernel_ms": round(best, 4), "gbs": round(2 * nbytes / 1e6 / best, 1),
                           "frac": round(2 * nbytes / 1e6 / best / peak, 3), "ok": ok}), flush=True)
 eng.close()

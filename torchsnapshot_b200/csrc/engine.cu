@@ -602,18 +602,26 @@ static int plan_wave(tsnap_job* job, Wave& w) {
                         w.tmaps.push_back(tp);
                     }
                 }
+                if (m.mode == kModeRows && m.bytes) {
+                    TmaPair tp;
+                    if (make_rows_tma_pair(m, &tp)) {  // short runs: a box of many runs per TMA request
+                        m.mode = kModeRowsTma;
+                        m.q_zero_point = int64_t(w.tmaps.size());
+                        w.tmaps.push_back(tp);
+                    }
+                }
                 const uint64_t nt = tile_count(m);
                 if (nt == 0) continue;
                 const uint32_t mi = uint32_t(w.members.size());
                 w.members.push_back(m);
-                std::vector<Tile>& tv = m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : m.mode == kModeStrided ? w.tiles_strided : m.mode == kModeTranspose ? w.tiles_transpose : m.mode == kModeTransposeTma ? w.tiles_tma : w.tiles_lsu;
-                (m.mode == kModeBulk ? job->stats.bytes_bulk : m.mode == kModeRows ? job->stats.bytes_rows : job->stats.bytes_lsu) += m.bytes;
+                std::vector<Tile>& tv = m.mode == kModeRowsTma ? w.tiles_rows_tma : m.mode == kModeBulk ? w.tiles_bulk : m.mode == kModeRows ? w.tiles_rows : m.mode == kModeStrided ? w.tiles_strided : m.mode == kModeTranspose ? w.tiles_transpose : m.mode == kModeTransposeTma ? w.tiles_tma : w.tiles_lsu;
+                (m.mode == kModeBulk ? job->stats.bytes_bulk : (m.mode == kModeRows || m.mode == kModeRowsTma) ? job->stats.bytes_rows : job->stats.bytes_lsu) += m.bytes;
                 for (uint64_t t = 0; t < nt; ++t) tv.push_back(Tile{mi, uint32_t(t)});
             }
         }
     }
     job->stats.n_tiles_bulk += w.tiles_bulk.size();
-    job->stats.n_tiles_rows += w.tiles_rows.size();
+    job->stats.n_tiles_rows += w.tiles_rows.size() + w.tiles_rows_tma.size();
     job->stats.n_tiles_lsu += w.tiles_lsu.size() + w.tiles_strided.size() + w.tiles_transpose.size() + w.tiles_tma.size();
     return TSNAP_OK;
 }
@@ -627,8 +635,8 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     const size_t lb = w.tiles_lsu.size() * sizeof(Tile);
     const size_t sb2 = w.tiles_strided.size() * sizeof(Tile);
     const size_t tb2 = w.tiles_transpose.size() * sizeof(Tile);
-    const size_t tmb = w.tiles_tma.size() * sizeof(Tile), mpb = w.tmaps.size() * sizeof(TmaPair);
-    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256) + align_up(tb2, 256) + align_up(tmb, 256) + align_up(mpb, 256);
+    const size_t tmb = w.tiles_tma.size() * sizeof(Tile), mpb = w.tmaps.size() * sizeof(TmaPair), rtb = w.tiles_rows_tma.size() * sizeof(Tile);
+    w.table_bytes = align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256) + align_up(tb2, 256) + align_up(tmb, 256) + align_up(mpb, 256) + align_up(rtb, 256);
     CUDA_TRY(cudaEventCreate(&w.ev_k0));
     CUDA_TRY(cudaEventCreate(&w.ev_k1));
     CUDA_TRY(cudaEventCreate(&w.ev_kr));
@@ -653,6 +661,7 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     Tile* d_transpose = reinterpret_cast<Tile*>(d + align_up(mb, 256) + align_up(bb, 256) + align_up(rb, 256) + align_up(lb, 256) + align_up(sb2, 256));
     Tile* d_tma = reinterpret_cast<Tile*>(reinterpret_cast<char*>(d_transpose) + align_up(tb2, 256));
     TmaPair* d_maps = reinterpret_cast<TmaPair*>(reinterpret_cast<char*>(d_tma) + align_up(tmb, 256));
+    Tile* d_rows_tma = reinterpret_cast<Tile*>(reinterpret_cast<char*>(d_maps) + align_up(mpb, 256));
     // pageable sources: the runtime stages them before returning, so the vectors may be freed later
     CUDA_TRY(cudaMemcpyAsync(d_members, w.members.data(), mb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (bb) CUDA_TRY(cudaMemcpyAsync(d_bulk, w.tiles_bulk.data(), bb, cudaMemcpyHostToDevice, eng->s_kernel));
@@ -662,11 +671,13 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     if (tb2) CUDA_TRY(cudaMemcpyAsync(d_transpose, w.tiles_transpose.data(), tb2, cudaMemcpyHostToDevice, eng->s_kernel));
     if (tmb) CUDA_TRY(cudaMemcpyAsync(d_tma, w.tiles_tma.data(), tmb, cudaMemcpyHostToDevice, eng->s_kernel));
     if (mpb) CUDA_TRY(cudaMemcpyAsync(d_maps, w.tmaps.data(), mpb, cudaMemcpyHostToDevice, eng->s_kernel));
-    job->stats.table_h2d_bytes += mb + bb + rb + lb + sb2 + tb2 + tmb + mpb;
+    if (rtb) CUDA_TRY(cudaMemcpyAsync(d_rows_tma, w.tiles_rows_tma.data(), rtb, cudaMemcpyHostToDevice, eng->s_kernel));
+    job->stats.table_h2d_bytes += mb + bb + rb + lb + sb2 + tb2 + tmb + mpb + rtb;
     CUDA_TRY(cudaEventRecord(w.ev_k0, eng->s_kernel));
     CUDA_TRY(launch_bulk(d_members, d_bulk, uint32_t(w.tiles_bulk.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_k1, eng->s_kernel));
     CUDA_TRY(launch_rows(d_members, d_rows, uint32_t(w.tiles_rows.size()), eng->sm_count, eng->s_kernel));
+    CUDA_TRY(launch_rows_tma(d_members, d_rows_tma, d_maps, uint32_t(w.tiles_rows_tma.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_kr, eng->s_kernel));
     CUDA_TRY(launch_lsu(d_members, d_lsu, uint32_t(w.tiles_lsu.size()), eng->sm_count, eng->s_kernel, kLsuDefault));
     CUDA_TRY(launch_lsu(d_members, d_strided, uint32_t(w.tiles_strided.size()), eng->sm_count, eng->s_kernel, kLsuStrided));
@@ -674,7 +685,7 @@ static int launch_wave(tsnap_job* job, Wave& w) {
     CUDA_TRY(launch_transpose_tma(d_members, d_tma, d_maps, uint32_t(w.tiles_tma.size()), eng->sm_count, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_k2, eng->s_kernel));
     CUDA_TRY(cudaEventRecord(w.ev_done, eng->s_kernel));
-    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1) + (w.tiles_strided.empty() ? 0 : 1) + (w.tiles_transpose.empty() ? 0 : 1) + (w.tiles_tma.empty() ? 0 : 1);
+    const int nl = (w.tiles_bulk.empty() ? 0 : 1) + (w.tiles_rows.empty() ? 0 : 1) + (w.tiles_lsu.empty() ? 0 : 1) + (w.tiles_strided.empty() ? 0 : 1) + (w.tiles_transpose.empty() ? 0 : 1) + (w.tiles_tma.empty() ? 0 : 1) + (w.tiles_rows_tma.empty() ? 0 : 1);
     job->stats.n_kernel_launches += nl;
     eng->kernels_launched += nl;
     return TSNAP_OK;

@@ -173,6 +173,7 @@ struct Wave {
     std::vector<Member> members;
     std::vector<Tile> tiles_bulk, tiles_rows, tiles_lsu, tiles_strided, tiles_transpose;  // the last two run their own builds of the LSU kernel
     std::vector<Tile> tiles_tma;    // kModeTransposeTma
+    std::vector<Tile> tiles_rows_tma;  // kModeRowsTma
     std::vector<TmaPair> tmaps;     // their tensor maps (Member.q_zero_point indexes this table)
     void* d_tables = nullptr;
     size_t table_bytes = 0, table_cap = 0;

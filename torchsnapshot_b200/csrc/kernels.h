@@ -25,7 +25,11 @@ cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t nt
 // or a driver without cuTensorMapEncodeTiled).
 bool transpose_tma_enabled();
 bool make_tma_pair(const Member& m, TmaPair* out, uint32_t* variant);  // variant = tile shape, for Member.shift bits 16-17
-cudaError_t init_transpose_tma();
+// kModeRowsTma: the same for kModeRows members with runs <= 1 KiB (TSNAP_B200_TMA_ROWS=0 keeps them on the per-run kernel)
+bool make_rows_tma_pair(const Member& m, TmaPair* out);
+cudaError_t launch_rows_tma(const Member* d_members, const Tile* d_tiles, const TmaPair* d_maps, uint32_t ntiles, int sm_count,
+                            cudaStream_t stream);
+cudaError_t init_transpose_tma();  // both tensor-map kernels
 cudaError_t launch_transpose_tma(const Member* d_members, const Tile* d_tiles, const TmaPair* d_maps, uint32_t ntiles, int sm_count,
                                  cudaStream_t stream);
 }  // namespace tsnap

@@ -256,6 +256,82 @@ tsnap_transpose_tma_kernel(const Member* __restrict__ members, const Tile* __res
     }
 }
 
+// ---- tsnap_rows_tma_kernel: kModeRowsTma ------------------------------------------------------------------------
+// Column shards / narrow views whose runs are short (<= kRowsTmaMaxRun = 1 KiB): the per-run copy-engine requests of the rows kernel are
+// bound by the request rate (~46 cycles each), a tensor map moves a box of up to 256 runs with ONE request on each side.
+// One lane per CTA drives a ring of 32 KiB stages, exactly like the dense bulk kernel: TMA tile load -> mbarrier ->
+// TMA tile store -> bulk group; nothing passes through registers.
+constexpr int kRtStages = 3;
+constexpr int kRtCtasPerSm = 2;
+constexpr uint32_t kRtSmemBytes = kRtStages * kTmaTileBytes + 1024 + 256;
+
+struct RtMeta {
+    int32_t c[5];
+    const void* dmap;
+};
+
+__device__ __forceinline__ void rt_coords(const Member& m, uint32_t index, int32_t (&c)[5]) {
+    const uint32_t rows = rows_tma_box_rows(m.inner);
+    const uint32_t last = m.nouter - 1;
+    const uint32_t tiles_r = (uint32_t)(((uint64_t)m.osize[last] + rows - 1) / rows);
+    uint32_t rest = index / tiles_r;
+    c[0] = 0;
+    c[1] = (int32_t)((index - rest * tiles_r) * rows);
+    c[2] = c[3] = c[4] = 0;
+    int k = 2;
+    for (int i = (int)last - 1; i >= 0; --i) {
+        const uint32_t sz = (uint32_t)m.osize[i];
+        c[k++] = (int32_t)(rest % sz);
+        rest /= sz;
+    }
+}
+
+__global__ void __launch_bounds__(32, kRtCtasPerSm)
+tsnap_rows_tma_kernel(const Member* __restrict__ members, const Tile* __restrict__ tiles, const TmaPair* __restrict__ maps, uint32_t ntiles) {
+    extern __shared__ unsigned char rt_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rt_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRtStages * kTmaTileBytes);
+    RtMeta* meta = reinterpret_cast<RtMeta*>(full + kRtStages);
+    if (threadIdx.x != 0) return;  // one elected lane drives the TMA unit
+
+    for (int s = 0; s < kRtStages; ++s) mbar_init(smem_u32(full + s), 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    const uint32_t first = blockIdx.x, step = gridDim.x;
+    const uint32_t n_my = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    uint32_t fenced_member = 0xffffffffu;
+    auto issue_load = [&](uint32_t k) {
+        const Tile tl = tiles[first + k * step];
+        const Member& m = members[tl.member];
+        const TmaPair* mp = maps + (uint32_t)m.q_zero_point;
+        if (tl.member != fenced_member) {
+            tensormap_acquire(mp->src);
+            tensormap_acquire(mp->dst);
+            fenced_member = tl.member;
+        }
+        const uint32_t s = k % kRtStages;
+        rt_coords(m, tl.index, meta[s].c);
+        meta[s].dmap = mp->dst;
+        const uint32_t bar = smem_u32(full + s);
+        mbar_expect_tx(bar, (uint32_t)m.inner * rows_tma_box_rows(m.inner));  // the whole box, clipped parts are zero-filled
+        tma_load_5d(smem_u32(smem + s * kTmaTileBytes), mp->src, meta[s].c, bar);
+    };
+    for (uint32_t k = 0; k < n_my && k < (uint32_t)kRtStages; ++k) issue_load(k);
+    for (uint32_t k = 0; k < n_my; ++k) {
+        const uint32_t s = k % kRtStages;
+        mbar_wait_bounded(smem_u32(full + s), (k / kRtStages) & 1);
+        fence_proxy_async_smem();
+        tma_store_5d(meta[s].dmap, meta[s].c, smem_u32(smem + s * kTmaTileBytes));
+        bulk_commit();
+        // the stage stored one iteration ago is free once all but the newest store group have read shared memory
+        if (k >= 1 && k - 1 + kRtStages < n_my) {
+            bulk_wait_read<1>();
+            issue_load(k - 1 + kRtStages);
+        }
+    }
+    bulk_wait_all<0>();
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -349,8 +425,64 @@ bool make_tma_pair(const Member& m, TmaPair* out, uint32_t* variant) {
 }
 
 cudaError_t init_transpose_tma() {
-    return cudaFuncSetAttribute(tsnap_transpose_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTtSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tsnap_transpose_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTtSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tsnap_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRtSmemBytes);
+    return e;
 }
+bool rows_tma_enabled() {
+    const char* e = getenv("TSNAP_B200_TMA_ROWS");
+    return !(e && e[0] == '0') && encode_tiled_fn() != nullptr;
+}
+
+bool make_rows_tma_pair(const Member& m, TmaPair* out) {
+    if (m.mode != kModeRows || !rows_tma_enabled()) return false;
+    if (m.inner == 0 || m.inner > kRowsTmaMaxRun || (m.inner & 15)) return false;
+    if (m.nouter < 1 || m.nouter > (uint32_t)kRowsTmaMaxOuter) return false;
+    if ((m.src | m.dst) & 15) return false;
+    cuuint64_t dim[5], str_s[4], str_d[4];
+    dim[0] = m.inner / 8;
+    uint64_t extent_s = m.inner, extent_d = m.inner;
+    int n = 1;
+    for (int i = (int)m.nouter - 1; i >= 0; --i, ++n) {
+        const int64_t sz = m.osize[i], ss = m.sstride[i], ds = m.dstride[i];
+        if (sz <= 0 || sz >= (int64_t(1) << 32)) return false;
+        if (ss <= 0 || (ss & 15) || ss >= (int64_t(1) << 40) || ds <= 0 || (ds & 15) || ds >= (int64_t(1) << 40)) return false;
+        dim[n] = cuuint64_t(sz);
+        str_s[n - 1] = cuuint64_t(ss);
+        str_d[n - 1] = cuuint64_t(ds);
+        extent_s = std::max<uint64_t>(extent_s, uint64_t(sz) * uint64_t(ss));
+        extent_d = std::max<uint64_t>(extent_d, uint64_t(sz) * uint64_t(ds));
+    }
+    const uint64_t pad_s = (extent_s + 15) & ~uint64_t(15), pad_d = (extent_d + 15) & ~uint64_t(15);
+    if (pad_s >= (uint64_t(1) << 40) || pad_d >= (uint64_t(1) << 40)) return false;
+    for (; n < 5; ++n) {
+        dim[n] = 1;
+        str_s[n - 1] = pad_s;
+        str_d[n - 1] = pad_d;
+    }
+    const cuuint32_t box[5] = {cuuint32_t(m.inner / 8), rows_tma_box_rows(m.inner), 1, 1, 1}, ones[5] = {1, 1, 1, 1, 1};
+    EncodeTiledFn enc = encode_tiled_fn();
+    CUtensorMap ms, md;
+    if (enc(&ms, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, reinterpret_cast<void*>(uintptr_t(m.src)), dim, str_s, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (enc(&md, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, reinterpret_cast<void*>(uintptr_t(m.dst)), dim, str_d, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    memcpy(out->src, &ms, 128);
+    memcpy(out->dst, &md, 128);
+    return true;
+}
+
+cudaError_t launch_rows_tma(const Member* d_members, const Tile* d_tiles, const TmaPair* d_maps, uint32_t ntiles, int sm_count,
+                            cudaStream_t stream) {
+    if (ntiles == 0) return cudaSuccess;
+    uint32_t grid = (uint32_t)sm_count * kRtCtasPerSm;
+    if (grid > ntiles) grid = ntiles;
+    tsnap_rows_tma_kernel<<<grid, 32, kRtSmemBytes, stream>>>(d_members, d_tiles, d_maps, ntiles);
+    return cudaGetLastError();
+}
+
 
 cudaError_t launch_transpose_tma(const Member* d_members, const Tile* d_tiles, const TmaPair* d_maps, uint32_t ntiles, int sm_count,
                                  cudaStream_t stream) {
