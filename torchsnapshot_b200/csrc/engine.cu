@@ -591,7 +591,7 @@ static int plan_wave(tsnap_job* job, Wave& w) {
             if (rc != TSNAP_OK) return set_err(rc, "member of " + f.path + ": " + err);
             for (int k = 0; k < nc.n; ++k) {
                 Member& m = nc.m[k];
-                if (m.mode == kModeTranspose && m.bytes) {
+                if (eng->allow_bulk && m.mode == kModeTranspose && m.bytes) {
                     // addresses are final here: transposes the TMA unit can address get their tensor maps and move to its kernel
                     TmaPair tp;
                     uint32_t variant = 0;

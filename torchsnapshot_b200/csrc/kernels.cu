@@ -8,6 +8,7 @@
 //       to back with no padding, T:batcher.py:307), strided views (narrow on dim != 0, transposes,
 //       reshard-on-load overlap boxes, T:io_preparers/sharded_tensor.py:285-298) and fused dtype
 //       casts.  Destination-aligned 16 B stores, widest naturally aligned loads.
+//   (transposes and short-run column shards the TMA unit can address: transpose_tma.cu)
 //
 // Both are persistent: grid = SMs x resident CTAs, tiles taken round-robin from a host-built tile
 // table (plan.h).  HBM-bound byte movement: algorithmic traffic = 2 x payload bytes.

@@ -15,6 +15,7 @@ cudaError_t launch_rows(const Member* d_members, const Tile* d_tiles, uint32_t n
 //   kLsuStrided   2 CTAs/SM, 128 registers: the strided gather keeps 8 independent 16 B loads per thread in flight without
 //                 spilling (0.66 vs 0.47 on 128 B runs)
 //   kLsuTranspose 6 CTAs/SM, 40 registers: 16 KiB tiles, more CTAs in different phases of the load -> shared -> store cycle
+//                 (the fallback for transposes the tensor-map kernel cannot take)
 enum LsuVariant { kLsuDefault = 0, kLsuStrided = 1, kLsuTranspose = 2 };
 cudaError_t launch_lsu(const Member* d_members, const Tile* d_tiles, uint32_t ntiles, int sm_count,
                        cudaStream_t stream, int variant);
