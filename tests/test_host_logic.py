@@ -199,3 +199,32 @@ def test_quantize_on_save_matches_torch_and_the_reference_format(tmp_path):
         for k in ("w", "wt", "u"):
             _, scale, _ = hook.tsnap_quant(f"m/{k}", st[k])
             assert (tgt[k] - st[k]).abs().max().item() <= scale * 0.5 + 1e-6, k
+
+
+@pytest.mark.parametrize("batching", [True, False])
+def test_async_take_counts_cpu_copies_against_the_memory_budget(tmp_path, monkeypatch, batching):
+    """async_take may hand control back while the engine still reads host memory, so CPU tensors get a private copy —
+    but only while the per-rank memory budget lasts (the reference gates staging on it, T:scheduler.py:259-281);
+    what does not fit is written out before async_take returns, from the caller's memory.  Either way the snapshot
+    holds the values at the time of the call."""
+    import torchsnapshot_b200 as B
+    from torchsnapshot_b200 import scheduler as S
+
+    monkeypatch.setenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES", str(3 << 20))
+    monkeypatch.setenv("TORCHSNAPSHOT_DISABLE_BATCHING", "0" if batching else "1")
+    tensors = {f"t{i}": torch.full((1 << 18,), float(i)) for i in range(8)}  # 8 x 1 MiB
+    expect = {k: v.clone() for k, v in tensors.items()}
+    pending = B.Snapshot.async_take(str(tmp_path / "s"), {"m": B.StateDict(**tensors)})
+    cloned, in_place = S.LAST_STATS["host_clone_bytes"], S.LAST_STATS["host_blocking_bytes"]
+    for v in tensors.values():
+        v.add_(100.0)  # the caller owns its memory again
+    snap = pending.wait()
+    assert cloned <= 3 << 20 and in_place >= 5 << 20 and cloned + in_place == 8 << 20, (cloned, in_place)
+    out = B.StateDict(**{k: torch.zeros_like(v) for k, v in tensors.items()})
+    snap.restore({"m": out})
+    for k, v in expect.items():
+        assert torch.equal(out[k], v), k
+    # with room for everything nothing blocks
+    monkeypatch.setenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES", str(64 << 20))
+    B.Snapshot.async_take(str(tmp_path / "s2"), {"m": B.StateDict(**tensors)}).wait()
+    assert S.LAST_STATS["host_blocking_bytes"] == 0 and S.LAST_STATS["host_clone_bytes"] == 8 << 20

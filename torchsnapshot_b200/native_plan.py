@@ -33,7 +33,35 @@ def _castable(src: torch.dtype, dst: torch.dtype) -> bool:
 
 
 # ---- save side -----------------------------------------------------------------------------------
-def _describe_tensor_stager(st: Any, offset: int) -> Optional[Described]:
+class HostCloneBudget:
+    """Host bytes ``async_take`` may spend on private copies of CPU tensors (the engine reads host memory after
+    ``async_take`` has returned, so the caller's tensor must not be the source).  The reference admits staging only while the
+    per-rank memory budget allows and lets ``async_take`` wait for writes to free it (T:scheduler.py:259-281); here a CPU
+    tensor that no longer fits is not copied at all: its request is marked blocking and written out before ``async_take``
+    returns, straight from the caller's memory."""
+
+    def __init__(self, nbytes: int) -> None:
+        self.remaining = max(0, int(nbytes))
+        self.cloned_bytes = 0
+        self.blocking_bytes = 0
+        self._blocking = False
+
+    def admit(self, nbytes: int) -> bool:
+        if self._blocking or nbytes > self.remaining:
+            self._blocking = True  # the rest of this request is read in place as well
+            self.blocking_bytes += nbytes
+            return False
+        self.remaining -= nbytes
+        self.cloned_bytes += nbytes
+        return True
+
+    def take_blocking(self) -> bool:
+        """Did the request described since the last call leave a CPU tensor uncopied?"""
+        b, self._blocking = self._blocking, False
+        return b
+
+
+def _describe_tensor_stager(st: Any, offset: int, clones: Optional[HostCloneBudget] = None) -> Optional[Described]:
     entry = getattr(st, "entry", None)
     tensor = getattr(st, "tensor", None)
     if entry is not None and isinstance(tensor, torch.Tensor) and getattr(st, "qparams", None) is not None:
@@ -62,11 +90,13 @@ def _describe_tensor_stager(st: Any, offset: int) -> Optional[Described]:
     if _native.needs_contiguous_copy(t):
         t = t.contiguous()
     elif getattr(st, "is_async_snapshot", False) and t.device.type == "cpu":
-        t = t.clone()  # host memory is read after async_take returned
+        # host memory is read after async_take returned: a private copy while the budget lasts, else a blocking request
+        if clones is None or clones.admit(t.numel() * t.element_size()):
+            t = t.clone()
     return [_native.save_desc(t, offset, wire_dtype=wire_dtype)], [t], nbytes
 
 
-def describe_stager(st: Any) -> Optional[Described]:
+def describe_stager(st: Any, clones: Optional[HostCloneBudget] = None) -> Optional[Described]:
     """(descriptors, keep-alive tensors, wire size) of one WriteReq's stager, or None when it has to go
     through its own ``stage_buffer`` (pickled objects, complex / quantized tensors, foreign stagers)."""
     members = getattr(st, "byte_range_to_buffer_stager", None)
@@ -75,14 +105,14 @@ def describe_stager(st: Any) -> Optional[Described]:
         keep: List[torch.Tensor] = []
         end = 0
         for (lo, hi), member in members.items():
-            one = _describe_tensor_stager(member, lo)
+            one = _describe_tensor_stager(member, lo, clones)
             if one is None or one[2] != hi - lo or lo != end:
                 return None
             descs += one[0]
             keep += one[1]
             end = hi
         return descs, keep, end
-    return _describe_tensor_stager(st, 0)
+    return _describe_tensor_stager(st, 0, clones)
 
 
 # ---- restore side ----------------------------------------------------------------------------------

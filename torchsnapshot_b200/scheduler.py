@@ -29,7 +29,7 @@ import torch
 from . import _native
 from .io_types import ReadIO, ReadReq, StoragePlugin, WriteIO, WriteReq
 from .knobs import get_max_per_rank_io_concurrency, get_memory_budget_override
-from .native_plan import describe_consumer, describe_stager, native_root as _native_root
+from .native_plan import HostCloneBudget, describe_consumer, describe_stager, native_root as _native_root
 from .pg_wrapper import PGWrapper
 
 logger = logging.getLogger(__name__)
@@ -139,16 +139,20 @@ LAST_STATS: Dict[str, object] = {}  # filled by the last executed plan; read by 
 
 
 class PendingIOWork:
-    def __init__(self, native: Optional[_NativeJobs], io_tasks: Set["asyncio.Task"], begin_ts: float, rank: int, nbytes: int) -> None:
+    def __init__(self, native: Optional[_NativeJobs], io_tasks: Set["asyncio.Task"], begin_ts: float, rank: int, nbytes: int,
+                 deferred_error: Optional[BaseException] = None) -> None:
         self.native = native
         self.io_tasks = io_tasks
         self.begin_ts = begin_ts
         self.rank = rank
         self.nbytes = nbytes
+        self.deferred_error = deferred_error  # a storage error of the blocking part: reported where async errors are
 
     async def complete(self) -> None:
         loop = asyncio.get_running_loop()
         try:
+            if self.deferred_error is not None:
+                raise self.deferred_error
             if self.io_tasks:
                 await asyncio.gather(*self.io_tasks)
             if self.native is not None:
@@ -180,17 +184,26 @@ async def execute_write_reqs(
     loop = asyncio.get_running_loop()
     root = _native_root(storage, "write")
     native: Optional[_NativeJobs] = None
+    blocking: Optional[_NativeJobs] = None  # async_take: CPU tensors beyond the clone budget, written before returning
+    clones = HostCloneBudget(memory_budget_bytes)
     generic: List[WriteReq] = []
     total = 0
     for wr in write_reqs:
-        described = describe_stager(wr.buffer_stager) if root is not None else None
+        described = describe_stager(wr.buffer_stager, clones) if root is not None else None
+        in_place = clones.take_blocking()
         if described is not None and not _one_device(described[1]):
             described = None
         if described is not None:
             descs, keep, nbytes = described
-            if native is None:
-                native = _NativeJobs(save=True)
-            job = native.job_for(_engine_key(keep))
+            if in_place:
+                if blocking is None:
+                    blocking = _NativeJobs(save=True)
+                group = blocking
+            else:
+                if native is None:
+                    native = _NativeJobs(save=True)
+                group = native
+            job = group.job_for(_engine_key(keep))
             fi = job.add_file(os.path.join(root, wr.path), nbytes)
             for d in descs:
                 job.add_member(fi, d)
@@ -202,6 +215,19 @@ async def execute_write_reqs(
     if native is not None:
         native.submit(memory_budget_bytes)
     lap("submit")
+    deferred_error: Optional[BaseException] = None
+    if blocking is not None:
+        # read from the caller's memory: these files are complete before control returns to the caller
+        try:
+            blocking.submit(memory_budget_bytes)
+            await loop.run_in_executor(None, blocking.wait)
+        except Exception as e:  # surfaced by PendingSnapshot.wait(), like every other storage error of async_take
+            deferred_error = e
+        finally:
+            blocking.destroy()
+        lap("blocking_host_writes")
+    LAST_STATS["host_clone_bytes"] = clones.cloned_bytes
+    LAST_STATS["host_blocking_bytes"] = clones.blocking_bytes
 
     # generic pipeline: budget-gated staging, bounded concurrent writes
     io_tasks: Set[asyncio.Task] = set()
@@ -255,7 +281,7 @@ async def execute_write_reqs(
     lap("wait_device")
     LAST_STATS["write_phases_ms"] = phases
     logger.info(f"Rank {rank} completed staging in {time.monotonic() - begin:.2f} seconds")
-    return PendingIOWork(native, io_tasks, begin, rank, total)
+    return PendingIOWork(native, io_tasks, begin, rank, total, deferred_error)
 
 
 def sync_execute_write_reqs(
