@@ -246,13 +246,16 @@ tsnap_transpose_tma_kernel(const Member* __restrict__ members, const Tile* __res
         unsigned char* out = out_buf + o * kTmaTileBytes;
         uint32_t r[8][4];
         TT_DISPATCH(kind, tt_read_blocks, in, r)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(empty + s));
         mbar_wait_bounded(smem_u32(out_free + o), ((k / kTtOut) & 1) ^ 1);  // passes at once on the stage's first use
         TT_DISPATCH(kind, tt_write_blocks, out, r)
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(out_full + o));
+        if (lane == 0) {
+            // the load stage is released only now: its values have provably left shared memory (the stores above consumed
+            // them), and the producer refills it after this tile's store anyway, so nothing is lost by not signalling earlier
+            mbar_arrive(smem_u32(empty + s));
+            mbar_arrive(smem_u32(out_full + o));
+        }
     }
 }
 
