@@ -228,3 +228,18 @@ def test_async_take_counts_cpu_copies_against_the_memory_budget(tmp_path, monkey
     monkeypatch.setenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES", str(64 << 20))
     B.Snapshot.async_take(str(tmp_path / "s2"), {"m": B.StateDict(**tensors)}).wait()
     assert S.LAST_STATS["host_blocking_bytes"] == 0 and S.LAST_STATS["host_clone_bytes"] == 8 << 20
+
+
+def test_async_take_blocking_part_reports_storage_errors_at_wait(tmp_path, monkeypatch):
+    """A storage error in the part async_take writes before returning (CPU tensors beyond the clone budget) surfaces where
+    every other storage error of async_take does: PendingSnapshot.wait() (T:tests/test_async_take.py:58-66)."""
+    import torchsnapshot_b200 as B
+
+    monkeypatch.setenv("TORCHSNAPSHOT_PER_RANK_MEMORY_BUDGET_BYTES", "1024")
+    monkeypatch.setenv("TORCHSNAPSHOT_DISABLE_BATCHING", "1")
+    blocker = tmp_path / "not_a_dir"
+    blocker.write_text("x")
+    pending = B.Snapshot.async_take(str(blocker / "snap"), {"m": B.StateDict(t=torch.ones(1 << 16))})
+    with pytest.raises(Exception):
+        pending.wait()
+    assert not (blocker / "snap").exists()

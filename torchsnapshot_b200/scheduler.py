@@ -151,8 +151,6 @@ class PendingIOWork:
     async def complete(self) -> None:
         loop = asyncio.get_running_loop()
         try:
-            if self.deferred_error is not None:
-                raise self.deferred_error
             if self.io_tasks:
                 await asyncio.gather(*self.io_tasks)
             if self.native is not None:
@@ -162,6 +160,8 @@ class PendingIOWork:
         finally:
             if self.native is not None:
                 self.native.destroy()
+        if self.deferred_error is not None:
+            raise self.deferred_error
         dt = max(time.monotonic() - self.begin_ts, 1e-9)
         logger.info(f"Rank {self.rank} completed writing in {dt:.2f} seconds (throughput {self.nbytes / 2**20 / dt:.2f}MB/s)")
 
